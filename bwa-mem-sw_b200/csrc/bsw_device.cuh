@@ -1,46 +1,62 @@
-// bsw_device.cuh -- device-side data layout shared by the host driver and the kernels.
+// bsw_device.cuh -- data layout in HBM shared by the host driver and the kernels.
+//
+// The reference moves a 256 KiB task batch into a BRAM (tbb.v:163-194) that task_parse walks word by
+// word (sw_pe_array_task_parse.v:924-948).  Here a batch is re-laid-out by the host scheduler into
+// "tiles" so that every device access is a coalesced 128-byte line:
+//
+//   K1 tile  = 32 extension tasks of similar shape, one per lane of a warp.
+//              query  words: q[k*32 + lane], k < nqw     (8 bases per u32, base j in bits 4*(j&7)..+3)
+//              target words: t[k*32 + lane], k < ntw
+//              so "word k of all 32 tasks" is one 128 B line, the whole query block is one contiguous
+//              range that a single TMA bulk copy drops into shared memory in exactly the layout the
+//              kernel uses (qs[k][lane]), and the target streams with one coalesced LDG per 8 rows.
+//   K2 tile  = 1 long task handled by a whole warp; query and target are stored one base per byte,
+//              contiguous, so lane l reads byte j0+l of a row: one coalesced 32-byte sector.
+//
+// Per-slot scalars are one int4 {qlen, tlen, h0, w} (w already clamped by ksw_extend2's
+// max_ins/max_del rule -- the RTL also receives it precomputed: proc_element.v:924-934); results are
+// two int4 per slot {score,qle,tle,gtle} {gscore,max_off,cells,status}; the host maps slot -> task.
 #pragma once
 #include <cstdint>
-#include <cuda_runtime.h>
 
 namespace bsw {
 
-// Per-chunk task table in HBM (structure of arrays, indexed by task id inside the chunk).
-//   qseq/tseq : bases packed 4 bit each, base j of a sequence in word j>>3, bits 4*(j&7)..+3
-//               (little-nibble first; the FPGA wire order -- first base in bits 31:28,
-//               proc_element.v:1638,1677 -- is converted by the level-3 adapter).  Every
-//               sequence starts on a 16-byte boundary and is zero-padded to a multiple of 16 bytes,
-//               and both arrays end with 32 bytes of slack, so kernels may over-read one uint4.
-//   qoffw/toffw : word offset of the task's first query/target word.
-//   w          : band width AFTER ksw_extend2's max_ins/max_del clamp (done on the host in double,
-//                exactly as BWA does; the RTL also receives it precomputed: proc_element.v:924-934).
-struct DevTasks {
-    const uint32_t* qseq;
-    const uint32_t* tseq;
-    const uint32_t* qoffw;
-    const uint32_t* toffw;
-    const int32_t*  qlen;
-    const int32_t*  tlen;
-    const int32_t*  h0;
-    const int32_t*  w;
-    int4*           out;      // 2 x int4 per task: {score,qle,tle,gtle} {gscore,max_off,cells,status}
+constexpr int TILE_LANES = 32;
+constexpr int K1_EH_SLACK = 8;      // row-buffer words past eh[qmax] that a partial chunk may over-read
+
+struct __attribute__((aligned(16))) TileHdr {
+    uint32_t qoff16;      // offset of the tile's query block in the sequence arena, in 16-byte units
+    uint32_t toff16;      // offset of the tile's target block, in 16-byte units
+    uint32_t nqw_ntw;     // K1: words per lane, query (low 16) | target (high 16).  K2: unused
+    uint32_t slot0;       // first slot of the tile (K1: 32 slots, K2: 1 slot)
+};
+
+struct __attribute__((aligned(16))) SlotParam { int32_t qlen, tlen, h0, w; };   // qlen == 0: padding lane
+
+struct __attribute__((aligned(16))) SlotResult {       // two 16-byte stores per task
+    int32_t score, qle, tle, gtle;                      // sw_extend return order (sw_pe_array_sw_extend.v:117-123)
+    int32_t gscore, max_off, cells, status;
 };
 
 // Scoring parameters (per batch).
 struct DevParams {
     int32_t o_del, e_del, o_ins, e_ins, zdrop;
-    int32_t match, mismatch;      // FAST scoring: +match / -mismatch (mismatch stored positive), valid iff fast_ok
-    uint32_t row_lo[5], row_hi[5];// GENERIC scoring: row t of the 5x5 matrix as bytes {s(t,0..3)} / {s(t,4),0,0,0}
+    int32_t match, mismatch;       // FAST scoring: +match / -mismatch (mismatch stored positive)
+    uint32_t row_lo[5], row_hi[5]; // GENERIC scoring: row t of the 5x5 matrix as bytes {s(t,0..3)} / {s(t,4),0,0,0}
+    int8_t  mat[28];               // the 5x5 matrix itself (K2 GENERIC lookup), padded
 };
 
-// One kernel launch = a slice [slot0, slot1) of `order` (task ids sorted by the scheduler).
+// One kernel launch = tiles [0, ntiles) of `tiles`.
 struct LaunchArgs {
-    DevTasks  t;
-    DevParams p;
-    const uint32_t* order;
-    uint32_t slot0, slot1;
-    int32_t  qmax;            // max qlen in the slice (sizes the per-thread row buffer)
-    unsigned long long* cells_total;   // device counter (atomicAdd once per warp)
+    const TileHdr*   tiles;
+    const SlotParam* slots;
+    const uint32_t*  arena;        // packed sequences, 16-byte aligned blocks
+    SlotResult*      out;          // indexed by slot
+    unsigned long long* cells_total;   // device counter of evaluated DP cells (one atomic per warp), may be null
+    DevParams        p;
+    uint32_t         ntiles;
+    int32_t          qmax;         // max qlen over the launch (sizes the per-lane row buffer)
+    int32_t          nqw_max;      // max query words per lane over the launch (K1)
 };
 
 constexpr int STATUS_OK = 0;

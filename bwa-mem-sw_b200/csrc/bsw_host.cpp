@@ -1,0 +1,763 @@
+// bsw_host.cpp -- libbsw.so: context, pinned staging, streams, level-1/2 batch calls (C ABI in include/bsw.h).
+//
+// Replaces the reference's transport + control plane for this path: the AAL/CCI session and CSR writes
+// (batch_manager.v:208-213,313-351), the task/result batch buffers (tbb.v, rbb.v) and the DSM busy-bit polling
+// (batch_manager.v:851-854) become pinned host buffers, cudaMemcpyAsync on per-device CUDA streams and events.
+// There is no CPU fallback: without a CUDA device bsw_init fails, and every batch call runs the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <future>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bsw.h"
+#include "bsw_device.cuh"
+#include "bsw_kernels.h"
+#include "bsw_sched.h"
+#include "bsw_internal.h"
+
+using namespace bsw;
+
+namespace {
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// One staging slot = one in-flight chunk on one stream.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    // pinned host staging
+    uint32_t* h_arena = nullptr;  size_t h_arena_cap = 0;
+    TileHdr* h_tiles = nullptr;   size_t h_tiles_cap = 0;
+    SlotParam* h_slots = nullptr; size_t h_slots_cap = 0;
+    SlotResult* h_out = nullptr;  size_t h_out_cap = 0;
+    // device
+    uint32_t* d_arena = nullptr;  size_t d_arena_cap = 0;
+    TileHdr* d_tiles = nullptr;   size_t d_tiles_cap = 0;
+    SlotParam* d_slots = nullptr; size_t d_slots_cap = 0;
+    SlotResult* d_out = nullptr;  size_t d_out_cap = 0;
+    unsigned long long* d_cells = nullptr;
+    unsigned long long* h_cells = nullptr;
+    // in-flight bookkeeping
+    bool busy = false;
+    Plan plan;
+    size_t first = 0, count = 0;     // chunk = tasks [first, first+count) of the batch
+    size_t nlaunch = 0;
+};
+
+struct Device {
+    int id = 0;
+    std::vector<Slot> slots;
+};
+
+}  // namespace
+
+struct bsw_ctx {
+    std::vector<Device> devs;
+    SchedOptions opt;
+    size_t chunk_tasks = 262144;
+    std::mutex mu;                 // serialises batch calls on this context
+    std::mutex err_mu;
+    std::string last_error;
+    bsw_stats stats{};
+    std::mutex async_mu;
+    struct Async { std::future<int> fut; uint32_t seq = 0; bool used = false; int status = 1; };
+    std::vector<Async> async;
+    uint32_t async_seq = 0;
+};
+
+struct bsw_resident {
+    int dev = 0;
+    Slot slot;
+    DevParams dp{};
+    int sym = 0;
+    size_t n = 0;
+    double last_ms = 0;
+};
+
+namespace {
+
+void set_error(bsw_ctx* ctx, const std::string& s)
+{
+    if (!ctx) return;
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    ctx->last_error = s;
+}
+
+int cuda_fail(bsw_ctx* ctx, cudaError_t e, const char* what)
+{
+    set_error(ctx, std::string(what) + ": " + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? BSW_ENOMEM : BSW_ECUDA;
+}
+
+#define CUDA_TRY(ctx, call)                                              \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #call);     \
+    } while (0)
+
+template <class T>
+int grow_pinned(bsw_ctx* ctx, T** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 64;
+    CUDA_TRY(ctx, cudaHostAlloc((void**)p, want * sizeof(T), cudaHostAllocDefault));
+    *cap = want;
+    return 0;
+}
+template <class T>
+int grow_device(bsw_ctx* ctx, T** p, size_t* cap, size_t need)
+{
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 64;
+    CUDA_TRY(ctx, cudaMalloc((void**)p, want * sizeof(T)));
+    *cap = want;
+    return 0;
+}
+
+int slot_init(bsw_ctx* ctx, Slot& s)
+{
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreate(&s.ev_k0));
+    CUDA_TRY(ctx, cudaEventCreate(&s.ev_k1));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaMalloc((void**)&s.d_cells, sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaHostAlloc((void**)&s.h_cells, sizeof(unsigned long long), cudaHostAllocDefault));
+    return 0;
+}
+
+void slot_free(Slot& s)
+{
+    if (s.h_arena) cudaFreeHost(s.h_arena);
+    if (s.h_tiles) cudaFreeHost(s.h_tiles);
+    if (s.h_slots) cudaFreeHost(s.h_slots);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.h_cells) cudaFreeHost(s.h_cells);
+    if (s.d_arena) cudaFree(s.d_arena);
+    if (s.d_tiles) cudaFree(s.d_tiles);
+    if (s.d_slots) cudaFree(s.d_slots);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_cells) cudaFree(s.d_cells);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, bool* fast_ok, int* max_mat)
+{
+    if (!p) { set_error(ctx, "params is null"); return BSW_EINVAL; }
+    if (p->e_del < 1 || p->e_ins < 1 || p->o_del < 0 || p->o_ins < 0 ||
+        p->e_del > 1000 || p->e_ins > 1000 || p->o_del > 10000 || p->o_ins > 10000) {
+        set_error(ctx, "gap penalties out of range (need 1 <= e <= 1000, 0 <= o <= 10000)");
+        return BSW_EINVAL;
+    }
+    memset(dp, 0, sizeof(*dp));
+    dp->o_del = p->o_del; dp->e_del = p->e_del; dp->o_ins = p->o_ins; dp->e_ins = p->e_ins; dp->zdrop = p->zdrop;
+    int mx = 0;
+    for (int k = 0; k < 25; ++k) { dp->mat[k] = p->mat[k]; mx = mx > p->mat[k] ? mx : p->mat[k]; }
+    *max_mat = mx;
+    // FAST scoring applies to N-free tasks when the 4x4 core is +a on the diagonal and -b elsewhere
+    bool fast = true;
+    const int a = p->mat[0], b = -p->mat[1];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (p->mat[5 * i + j] != (i == j ? a : -b)) fast = false;
+    *fast_ok = fast;
+    dp->match = a; dp->mismatch = b;
+    for (int t = 0; t < 5; ++t) {
+        uint32_t lo = 0;
+        for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)p->mat[5 * t + q] << (8 * q);
+        dp->row_lo[t] = lo;
+        dp->row_hi[t] = (uint32_t)(uint8_t)p->mat[5 * t + 4];
+    }
+    *sym = (p->o_del == p->o_ins && p->e_del == p->e_ins) ? 1 : 0;
+    return 0;
+}
+
+// Schedule + pack tasks [first, first+count) into the slot's pinned staging, then enqueue H2D, kernels and D2H.
+int slot_submit(bsw_ctx* ctx, Slot& s, const ExtTask* tasks, const uint8_t* cls, size_t first, size_t count,
+                const DevParams& dp, int sym, const SchedOptions& opt, bool timing)
+{
+    const double t0 = now_ms();
+    build_plan(tasks + first, cls + first, count, opt, &s.plan);
+    Plan& P = s.plan;
+    int rc;
+    if ((rc = grow_pinned(ctx, &s.h_arena, &s.h_arena_cap, P.arena_words))) return rc;
+    if ((rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, P.tiles.size()))) return rc;
+    if ((rc = grow_pinned(ctx, &s.h_slots, &s.h_slots_cap, P.slots.size()))) return rc;
+    if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, P.slots.size()))) return rc;
+    if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.arena_words))) return rc;
+    if ((rc = grow_device(ctx, &s.d_tiles, &s.d_tiles_cap, P.tiles.size()))) return rc;
+    if ((rc = grow_device(ctx, &s.d_slots, &s.d_slots_cap, P.slots.size()))) return rc;
+    if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, P.slots.size()))) return rc;
+    pack_arena(tasks + first, P, opt, s.h_arena);
+    memcpy(s.h_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
+    memcpy(s.h_slots, P.slots.data(), P.slots.size() * sizeof(SlotParam));
+    const double t1 = now_ms();
+
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_arena, s.h_arena, P.arena_words * 4, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_tiles, s.h_tiles, P.tiles.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_slots, s.h_slots, P.slots.size() * sizeof(SlotParam), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    s.nlaunch = 0;
+    for (const Launch& L : P.launches) {
+        LaunchArgs a{};
+        a.tiles = s.d_tiles + L.tile0; a.slots = s.d_slots; a.arena = s.d_arena; a.out = s.d_out;
+        a.cells_total = s.d_cells; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+        cudaError_t e = (L.kind == 1) ? k1_launch(a, opt.variant, L.generic, sym, s.stream)
+                                      : k2_launch(a, L.generic, s.stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : "K2 launch");
+        ++s.nlaunch;
+    }
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, P.slots.size() * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
+    s.busy = true; s.first = first; s.count = count;
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->stats.pack_ms += t1 - t0;
+        ctx->stats.h2d_bytes += P.arena_words * 4 + P.tiles.size() * sizeof(TileHdr) + P.slots.size() * sizeof(SlotParam);
+        ctx->stats.d2h_bytes += P.slots.size() * sizeof(SlotResult) + 8;
+        ctx->stats.kernel_launches += s.nlaunch;
+    }
+    return 0;
+}
+
+// Wait for the slot's chunk and scatter its results to out[first + task].
+int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, const SchedOptions& opt, bool timing)
+{
+    if (!s.busy) return 0;
+    CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
+    s.busy = false;
+    float ms = 0.f;
+    if (timing) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    const Plan& P = s.plan;
+    const size_t nslots = P.slots.size();
+    const size_t first = s.first;
+    const SlotResult* h_out = s.h_out;
+    std::atomic<int> bad(0);
+    pfor(nslots, 8192, opt.host_threads, [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            const int64_t t = P.slot_task[k];
+            if (t < 0) continue;
+            const SlotResult& r = h_out[k];
+            if (r.status != STATUS_OK) bad.store(1);
+            bsw_result& o = out[first + (size_t)t];
+            o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
+            if (cells) cells[first + (size_t)t] = (uint32_t)r.cells;
+        }
+    });
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->stats.tasks += s.count;
+        ctx->stats.cells_band += *s.h_cells;
+        ctx->stats.kernel_ms += ms;
+    }
+    if (bad.load()) { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
+    return 0;
+}
+
+// The engine behind every batch entry point: validate, shard over devices, pipeline chunks over stream slots.
+int run_extensions(bsw_ctx* ctx, const bsw_params* params, const ExtTask* tasks, size_t n, bsw_result* out, uint32_t* cells)
+{
+    if (!ctx || !out || (!tasks && n)) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (n == 0) return BSW_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const double w0 = now_ms();
+    DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
+    int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
+    if (rc) return rc;
+    SchedOptions opt = ctx->opt;
+    opt.fast_matrix = fast_ok;
+    if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
+
+    std::vector<uint8_t> cls(n);
+    size_t bad = 0; std::string msg;
+    rc = validate_tasks(tasks, n, max_mat, opt, cls.data(), &bad, &msg);
+    if (rc) { set_error(ctx, msg); return rc; }
+
+    // shard over devices by estimated cells (contiguous ranges), then chunk
+    const size_t ndev = ctx->devs.size();
+    std::vector<size_t> cut(ndev + 1, n);
+    cut[0] = 0;
+    if (ndev > 1) {
+        std::vector<uint64_t> pre(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) {
+            const int64_t band = std::min<int64_t>(tasks[i].qlen, 2 * (int64_t)tasks[i].w + 1);
+            pre[i + 1] = pre[i] + (uint64_t)(band * tasks[i].tlen) + 64;
+        }
+        for (size_t d = 1; d < ndev; ++d) {
+            const uint64_t target = pre[n] / ndev * d;
+            cut[d] = (size_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+            if (cut[d] < cut[d - 1]) cut[d] = cut[d - 1];
+            if (cut[d] > n) cut[d] = n;
+        }
+    }
+    std::vector<int> dev_rc(ndev, 0);
+    SchedOptions dopt = opt;
+    dopt.host_threads = std::max(1, opt.host_threads / (int)ndev);
+    auto dev_worker = [&](size_t d) {
+        Device& D = ctx->devs[d];
+        if (cudaSetDevice(D.id) != cudaSuccess) { dev_rc[d] = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); return; }
+        size_t pos = cut[d];
+        const size_t end = cut[d + 1];
+        size_t k = 0;
+        int r = 0;
+        while (pos < end && !r) {
+            Slot& s = D.slots[k % D.slots.size()];
+            r = slot_collect(ctx, s, out, cells, dopt, true);
+            if (r) break;
+            const size_t cnt = std::min(ctx->chunk_tasks, end - pos);
+            r = slot_submit(ctx, s, tasks, cls.data(), pos, cnt, dp, sym, dopt, true);
+            pos += cnt; ++k;
+        }
+        for (Slot& s : D.slots) {
+            const int r2 = slot_collect(ctx, s, out, cells, dopt, true);
+            if (!r) r = r2;
+        }
+        if (r) {                      // leave the device quiescent on error
+            for (Slot& s : D.slots) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }
+        }
+        dev_rc[d] = r;
+    };
+    if (ndev == 1) dev_worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < ndev; ++d) th.emplace_back(dev_worker, d);
+        for (auto& t : th) t.join();
+    }
+    for (size_t d = 0; d < ndev; ++d) if (dev_rc[d]) return dev_rc[d];
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->stats.wall_ms += now_ms() - w0;
+    }
+    return BSW_OK;
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+
+extern "C" {
+
+const char* bsw_version(void) { return "bsw-b200 0.1 (sm_100a)"; }
+
+int bsw_init(bsw_ctx** out, const int* device_ids, int n_devices, int streams_per_device)
+{
+    if (!out) return BSW_EINVAL;
+    *out = nullptr;
+    int ndev_avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev_avail);
+    if (e != cudaSuccess || ndev_avail <= 0) return BSW_ECUDA;       // no CPU fallback: no device, no context
+    std::unique_ptr<bsw_ctx> ctx(new bsw_ctx());
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return BSW_ECUDA;
+        ids.push_back(cur);
+    } else {
+        for (int k = 0; k < n_devices; ++k) {
+            if (device_ids[k] < 0 || device_ids[k] >= ndev_avail) return BSW_EINVAL;
+            ids.push_back(device_ids[k]);
+        }
+    }
+    if (streams_per_device <= 0) streams_per_device = 2;
+    if (streams_per_device > 8) streams_per_device = 8;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int id : ids) {
+        if (cudaSetDevice(id) != cudaSuccess) return BSW_ECUDA;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, id) != cudaSuccess) return BSW_ECUDA;
+        if (prop.major < 10) return BSW_ECUDA;                       // kernels are built for sm_100a only
+        Device D; D.id = id;
+        D.slots.resize((size_t)streams_per_device);
+        ctx->devs.push_back(std::move(D));
+        for (Slot& s : ctx->devs.back().slots)
+            if (slot_init(ctx.get(), s)) { bsw_destroy(ctx.release()); cudaSetDevice(prev); return BSW_ECUDA; }
+    }
+    cudaSetDevice(prev);
+    ctx->async.resize(16);
+    *out = ctx.release();
+    return BSW_OK;
+}
+
+void bsw_destroy(bsw_ctx* ctx)
+{
+    if (!ctx) return;
+    for (auto& a : ctx->async) if (a.used && a.fut.valid()) a.fut.wait();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (Device& D : ctx->devs) {
+        cudaSetDevice(D.id);
+        for (Slot& s : D.slots) { if (s.stream) cudaStreamSynchronize(s.stream); slot_free(s); }
+    }
+    cudaSetDevice(prev);
+    delete ctx;
+}
+
+const char* bsw_last_error(const bsw_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int bsw_num_devices(const bsw_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
+{
+    if (!ctx || !key) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const std::string k(key);
+    if (k == "variant") { if (value != 1 && value != 2) return BSW_EINVAL; ctx->opt.variant = (int)value; }
+    else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
+    else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
+    else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
+    else { set_error(ctx, "unknown option " + k); return BSW_EINVAL; }
+    return BSW_OK;
+}
+
+int bsw_extend_batch(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tasks, size_t n, bsw_result* out)
+{
+    if (!ctx) return BSW_EINVAL;
+    if (n == 0) return BSW_OK;
+    if (!params || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
+    std::vector<ExtTask> v(n);
+    const int nt = ctx->opt.host_threads;
+    pfor(n, 16384, nt, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const bsw_task& t = tasks[i];
+            ExtTask& x = v[i];
+            x.q = t.query; x.t = t.target; x.qlen = t.qlen; x.tlen = t.tlen; x.h0 = t.h0;
+            x.w = (t.qlen >= 1 && t.w >= 0) ? clamp_band(params->mat, t.qlen, t.w, params->end_bonus, params->o_ins,
+                                                         params->e_ins, params->o_del, params->e_del) : -1;
+        }
+    });
+    return run_extensions(ctx, params, v.data(), n, out, nullptr);
+}
+
+int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t* qbuf, const int64_t* qoff,
+                          const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
+                          bsw_result* out, uint32_t* cells)
+{
+    if (!ctx) return BSW_EINVAL;
+    if (n == 0) return BSW_OK;
+    if (!params || !qbuf || !qoff || !tbuf || !toff || !h0 || !w || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
+    std::vector<ExtTask> v(n);
+    std::atomic<int> bad(0);
+    pfor(n, 16384, ctx->opt.host_threads, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            ExtTask& x = v[i];
+            const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+            if (ql < 0 || tl < 0 || ql > 0x7fffffff || tl > 0x7fffffff) bad.store(1);
+            x.q = qbuf + qoff[i]; x.t = tbuf + toff[i];
+            x.qlen = (int32_t)std::max<int64_t>(std::min<int64_t>(ql, 0x7fffffff), -1);
+            x.tlen = (int32_t)std::max<int64_t>(std::min<int64_t>(tl, 0x7fffffff), -1);
+            x.h0 = h0[i];
+            x.w = (x.qlen >= 1 && w[i] >= 0) ? clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins,
+                                                          params->e_ins, params->o_del, params->e_del) : -1;
+        }
+    });
+    if (bad.load()) { set_error(ctx, "offsets are not monotone"); return BSW_EINVAL; }
+    return run_extensions(ctx, params, v.data(), n, out, cells);
+}
+
+// ---------------- level 2: fused seed task (left + right extension, band retry, clip) ----------------
+// Host-orchestrated in four device passes: left try 0, left try 1 (the few tasks whose max_off asks for the doubled
+// band, sw_pe_array_sw_extend.v:1963,1824-1825,1969-1970), right try 0 with h0 = left score
+// (sw_pe_array_proc_element.v:1671,1652), right try 1.  The clip decision (pe:1672-1675) runs on the host.
+#define BSW_MAX_BAND_TRY 2
+
+int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
+                       const bsw_seed_clamp* clamps, bsw_aln_record* out)
+{
+    if (!ctx) return BSW_EINVAL;
+    if (n == 0) return BSW_OK;
+    if (!P || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (P->p.e_ins < 1 || P->p.e_del < 1 || P->w < 0) { set_error(ctx, "bad parameters"); return BSW_EINVAL; }
+    struct St { int sc0, score, truesc, qb, qe, rb, re, aw[2]; };
+    std::vector<St> st(n);
+    for (size_t i = 0; i < n; ++i) {                                      // pe:471-475,581-583,...,783-797
+        const bsw_seed_task& s = tasks[i];
+        if (s.qlen[0] < 0 || s.qlen[1] < 0) { set_error(ctx, "negative flank length"); return BSW_EINVAL; }
+        st[i] = St{ s.init_score, 0, s.init_score, 0, s.qlen[1], 0, 0, { P->w, P->w } };
+    }
+    std::vector<ExtTask> ext;
+    std::vector<size_t> who;
+    std::vector<bsw_result> res, cur(n);
+    std::vector<int> a_score(n), prev(n);
+    for (int side = 0; side < 2; ++side) {                                // pe:1597,1622
+        bsw_params pp = P->p;
+        const int pen_clip = side ? P->pen_clip3 : P->pen_clip5;
+        pp.end_bonus = pen_clip;                                          // BWA passes pen_clip5/3 as ksw_extend2's end_bonus
+        std::vector<size_t> active;
+        for (size_t i = 0; i < n; ++i)
+            if (tasks[i].qlen[side] > 0) { active.push_back(i); a_score[i] = st[i].sc0; }      // pe:1670
+        for (int k = 0; k < BSW_MAX_BAND_TRY && !active.empty(); ++k) {   // sx:1963,1878
+            ext.clear(); who.clear();
+            const int aw = P->w << k;                                     // sx:1765
+            for (size_t i : active) {
+                const bsw_seed_task& s = tasks[i];
+                ExtTask x;
+                x.q = side ? s.q_right : s.q_left; x.t = side ? s.t_right : s.t_left;
+                x.qlen = s.qlen[side]; x.tlen = s.tlen[side];
+                x.h0 = side ? st[i].sc0 : s.h0;                           // pe:1671,1652
+                if (clamps)       // wire format: max_ins/max_del arrive precomputed from the host (pe:924-934; sx:1763-1765)
+                    x.w = std::min(aw, std::min(clamps[i].max_ins[side], clamps[i].max_del[side]));
+                else
+                    x.w = clamp_band(pp.mat, x.qlen, aw, pp.end_bonus, pp.o_ins, pp.e_ins, pp.o_del, pp.e_del);
+                ext.push_back(x); who.push_back(i);
+            }
+            res.resize(ext.size());
+            const int rc = run_extensions(ctx, &pp, ext.data(), ext.size(), res.data(), nullptr);
+            if (rc) return rc;
+            std::vector<size_t> again;
+            for (size_t e = 0; e < who.size(); ++e) {
+                const size_t i = who[e];
+                prev[i] = a_score[i];                                     // sx:1822,1859
+                a_score[i] = res[e].score; cur[i] = res[e]; st[i].aw[side] = aw;
+                if (!(a_score[i] == prev[i] || res[e].max_off < (aw >> 1) + (aw >> 2))) again.push_back(i);   // sx:1824-1825,1969-1970,1837
+            }
+            active.swap(again);
+        }
+        for (size_t i = 0; i < n; ++i) {
+            const bsw_seed_task& s = tasks[i];
+            if (s.qlen[side] <= 0) continue;
+            St& S = st[i];
+            const bsw_result& r = cur[i];
+            const int sc = a_score[i];
+            if (r.gscore <= 0 || r.gscore <= sc - pen_clip) {             // local: pe:1672,1674-1675,1667
+                if (side == 0) { S.qb = s.qbeg - r.qle; S.rb = -r.tle; S.truesc = sc; }          // pe:591-599,659-667,767-777
+                else           { S.qe = r.qle; S.re = r.tle; S.truesc += sc - S.sc0; }            // pe:615-623,683-691,1679-1680
+            } else {                                                      // to-end
+                if (side == 0) { S.qb = 0; S.rb = -r.gtle; S.truesc = r.gscore; }
+                else           { S.qe = s.qlen[1]; S.re = r.gtle; S.truesc += r.gscore - S.sc0; }
+            }
+            S.score = S.sc0 = sc;                                         // pe:697-700,727-728,1594,1685
+        }
+    }
+    for (size_t i = 0; i < n; ++i) {                                      // pe:1187-1205,1662-1665
+        const St& S = st[i];
+        bsw_aln_record& r = out[i];
+        r.id = tasks[i].id; r.qb = S.qb; r.qe = S.qe; r.rb = S.rb; r.re = S.re;
+        r.score = S.score; r.truesc = S.truesc; r.w = S.aw[0] > S.aw[1] ? S.aw[0] : S.aw[1];      // pe:1669,1684
+    }
+    return BSW_OK;
+}
+
+int bsw_chain2aln_batch(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n, bsw_aln_record* out)
+{
+    return bsw_chain2aln_impl(ctx, P, tasks, n, nullptr, out);
+}
+
+void bsw_set_error_text(bsw_ctx* ctx, const char* text) { set_error(ctx, text ? text : ""); }
+
+// ---------------- async pair ----------------
+int bsw_submit(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tasks, size_t n, bsw_result* out, bsw_ticket* ticket)
+{
+    if (!ctx || !ticket) return BSW_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->async_mu);
+    for (size_t k = 0; k < ctx->async.size(); ++k) {
+        auto& a = ctx->async[k];
+        if (a.used) continue;
+        a.used = true; a.seq = ++ctx->async_seq; a.status = 1;
+        const bsw_params pcopy = params ? *params : bsw_params{};
+        const bool have_params = params != nullptr;
+        a.fut = std::async(std::launch::async, [=]() { return bsw_extend_batch(ctx, have_params ? &pcopy : nullptr, tasks, n, out); });
+        ticket->slot = (int32_t)k; ticket->seq = a.seq;
+        return BSW_OK;
+    }
+    set_error(ctx, "no free async slot");
+    return BSW_EBUSY;
+}
+
+static int async_finish(bsw_ctx* ctx, const bsw_ticket* t, bool block)
+{
+    if (!ctx || !t || t->slot < 0 || (size_t)t->slot >= ctx->async.size()) return BSW_EINVAL;
+    std::unique_lock<std::mutex> g(ctx->async_mu);
+    auto& a = ctx->async[(size_t)t->slot];
+    if (!a.used || a.seq != t->seq) return BSW_EINVAL;
+    if (!block && a.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return 0;
+    std::future<int> f = std::move(a.fut);
+    g.unlock();
+    const int rc = f.get();
+    g.lock();
+    a.used = false;
+    return block ? rc : (rc == BSW_OK ? 1 : rc);
+}
+
+int bsw_poll(bsw_ctx* ctx, const bsw_ticket* ticket) { return async_finish(ctx, ticket, false); }
+int bsw_wait(bsw_ctx* ctx, const bsw_ticket* ticket) { return async_finish(ctx, ticket, true); }
+
+// ---------------- device-resident batches ----------------
+int bsw_resident_create(bsw_ctx* ctx, const bsw_params* params, const uint8_t* qbuf, const int64_t* qoff,
+                        const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
+                        bsw_resident** out)
+{
+    if (!ctx || !out) return BSW_EINVAL;
+    *out = nullptr;
+    if (!params || !qbuf || !qoff || !tbuf || !toff || !h0 || !w || n == 0) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_ptr<bsw_resident> R(new bsw_resident());
+    int max_mat = 0; bool fast_ok = false;
+    int rc = make_dev_params(ctx, params, &R->dp, &R->sym, &fast_ok, &max_mat);
+    if (rc) return rc;
+    SchedOptions opt = ctx->opt;
+    opt.fast_matrix = fast_ok;
+    if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
+    std::vector<ExtTask> v(n);
+    for (size_t i = 0; i < n; ++i) {
+        ExtTask& x = v[i];
+        x.q = qbuf + qoff[i]; x.t = tbuf + toff[i];
+        x.qlen = (int32_t)(qoff[i + 1] - qoff[i]); x.tlen = (int32_t)(toff[i + 1] - toff[i]); x.h0 = h0[i];
+        x.w = (x.qlen >= 1 && w[i] >= 0) ? clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins,
+                                                      params->e_ins, params->o_del, params->e_del) : -1;
+    }
+    std::vector<uint8_t> cls(n);
+    size_t bad = 0; std::string msg;
+    rc = validate_tasks(v.data(), n, max_mat, opt, cls.data(), &bad, &msg);
+    if (rc) { set_error(ctx, msg); return rc; }
+    R->dev = ctx->devs[0].id; R->n = n;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(R->dev));
+    rc = slot_init(ctx, R->slot);
+    if (!rc) {
+        // submit once: this packs, uploads and runs the batch; later runs reuse the device-resident plan
+        rc = slot_submit(ctx, R->slot, v.data(), cls.data(), 0, n, R->dp, R->sym, opt, true);
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(R->slot.stream); if (e != cudaSuccess) rc = cuda_fail(ctx, e, "resident upload"); }
+        R->slot.busy = false;
+    }
+    cudaSetDevice(prev);
+    if (rc) { slot_free(R->slot); return rc; }
+    *out = R.release();
+    return BSW_OK;
+}
+
+int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t* cells, uint64_t* launches)
+{
+    if (!ctx || !R) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(R->dev));
+    Slot& s = R->slot;
+    const Plan& P = s.plan;
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    size_t nl = 0;
+    for (const Launch& L : P.launches) {
+        LaunchArgs a{};
+        a.tiles = s.d_tiles + L.tile0; a.slots = s.d_slots; a.arena = s.d_arena; a.out = s.d_out;
+        a.cells_total = s.d_cells; a.p = R->dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+        cudaError_t e = (L.kind == 1) ? k1_launch(a, ctx->opt.variant, L.generic, R->sym, s.stream)
+                                      : k2_launch(a, L.generic, s.stream);
+        if (e != cudaSuccess) { cudaSetDevice(prev); return cuda_fail(ctx, e, "resident launch"); }
+        ++nl;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    R->last_ms = ms;
+    if (kernel_ms) *kernel_ms = ms;
+    if (cells) *cells = *s.h_cells;
+    if (launches) *launches = nl;
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->stats.tasks += R->n; ctx->stats.cells_band += *s.h_cells; ctx->stats.kernel_ms += ms; ctx->stats.kernel_launches += nl;
+    }
+    cudaSetDevice(prev);
+    return BSW_OK;
+}
+
+int bsw_resident_fetch(bsw_ctx* ctx, bsw_resident* R, bsw_result* out, uint32_t* cells)
+{
+    if (!ctx || !R || !out) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(R->dev));
+    Slot& s = R->slot;
+    const Plan& P = s.plan;
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, P.slots.size() * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
+    for (size_t k = 0; k < P.slots.size(); ++k) {
+        const int64_t t = P.slot_task[k];
+        if (t < 0) continue;
+        const SlotResult& r = s.h_out[k];
+        bsw_result& o = out[(size_t)t];
+        o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
+        if (cells) cells[(size_t)t] = (uint32_t)r.cells;
+    }
+    cudaSetDevice(prev);
+    return BSW_OK;
+}
+
+void bsw_resident_free(bsw_ctx* ctx, bsw_resident* R)
+{
+    if (!R) return;
+    (void)ctx;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(R->dev);
+    if (R->slot.stream) cudaStreamSynchronize(R->slot.stream);
+    slot_free(R->slot);
+    cudaSetDevice(prev);
+    delete R;
+}
+
+int bsw_get_stats(bsw_ctx* ctx, bsw_stats* out)
+{
+    if (!ctx || !out) return BSW_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    *out = ctx->stats;
+    return BSW_OK;
+}
+
+int bsw_reset_stats(bsw_ctx* ctx)
+{
+    if (!ctx) return BSW_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    ctx->stats = bsw_stats{};
+    return BSW_OK;
+}
+
+int bsw_measure_int_peak(bsw_ctx* ctx, int device_index, bsw_int_peak* out)
+{
+    if (!ctx || !out || device_index < 0 || (size_t)device_index >= ctx->devs.size()) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)device_index].id));
+    double ops[5] = { 0, 0, 0, 0, 0 }; double mhz = 0; int sms = 0;
+    cudaError_t e = int_peak_run(ops, &mhz, &sms, ctx->devs[(size_t)device_index].slots[0].stream);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "int peak micro-benchmark");
+    out->iadd_tops = ops[0] * 1e-12; out->vimnmx_tops = ops[1] * 1e-12; out->dpx_tops = ops[2] * 1e-12; out->mix_tops = ops[3] * 1e-12; out->dual_tops = ops[4] * 1e-12;
+    out->sm_clock_mhz = mhz; out->sm_count = sms;
+    return BSW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// bsw_k1_core.cuh -- one extension task as executed by one lane of the inter-task kernel K1.
+//
+// This is the body of what one FPGA PE runs for one sw_extend call (sw_pe_array_sw_extend.v FSM
+// :1639-1705).  It is written as a __host__ __device__ function over the K1 tile layout
+// (bsw_device.cuh) so that tests/emu can execute the *identical* control flow and arithmetic on the
+// CPU (tests only; the product library contains only the device instantiation).
+//
+// Row state.  BWA's eh_t eh[qlen+1] / the RTL's eh_arr ({E[15:8],H[7:0]}, sw_pe_array_sw_extend_eh_arr.v)
+// is one 32-bit word {E[31:16], H[15:0]} per column in shared memory at eh[j*32 + lane]: a warp's 32
+// tasks always hit 32 different banks, whatever column each lane is at.  Scores are < 32768 by the
+// scheduler's admission rule (h0 + qlen*max(mat) <= 32767), so 16 bits are exact.
+//
+// Band narrowing (V1).  The reference recomputes [beg,end) after every row by scanning the stored
+// row for the run of non-zero H around mj (sw_pe_array_sw_extend.v:1766-1769,1779,1782-1789).  A
+// second pass over the row would double the shared-memory traffic, so K1 applies the same rule lazily
+// inside the NEXT row, which reads every eh[j].h of the candidate window [beg, end+1) anyway:
+//   * a zero at column j <= mj means beg' >= j+1  -> the row restarts at j+1 (f=0, h1=first column)
+//   * a zero at column j >= mj+2 means end' = j    -> the row ends at j
+// Cells evaluated before a restart only touch eh[] slots left of beg', which are never read again
+// (beg is monotone), so the visible result -- including the cells count -- is bit-identical.
+// Chunks of 8 columns whose H are all non-zero (the common case inside the run) take a branch-free
+// path built from DPX fused add-max instructions (VIADDMNMX, also in its packed s16x2 form).
+#pragma once
+#include "bsw_device.cuh"
+
+#if defined(__CUDACC__)
+#define BSW_HD __host__ __device__ __forceinline__
+#else
+#define BSW_HD inline
+#endif
+
+namespace bsw {
+
+// ---- integer helpers: DPX intrinsics on the device, plain C on the host emulation ----
+BSW_HD int imax(int a, int b) { return a > b ? a : b; }
+BSW_HD int imin(int a, int b) { return a < b ? a : b; }
+
+BSW_HD int add_max(int a, int b, int c)        // max(a + b, c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s32(a, b, c);
+#else
+    return imax(a + b, c);
+#endif
+}
+BSW_HD int add_max_relu(int a, int b, int c)   // max(a + b, c, 0)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s32_relu(a, b, c);
+#else
+    return imax(imax(a + b, c), 0);
+#endif
+}
+BSW_HD uint32_t add_max_s16x2(uint32_t a, uint32_t b, uint32_t c)   // per 16-bit half: max(a + b, c), wrapping add
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2(a, b, c);
+#else
+    const int16_t lo = (int16_t)(uint16_t)((a & 0xffffu) + (b & 0xffffu));
+    const int16_t hi = (int16_t)(uint16_t)((a >> 16) + (b >> 16));
+    const int16_t clo = (int16_t)(uint16_t)(c & 0xffffu), chi = (int16_t)(uint16_t)(c >> 16);
+    const uint16_t rlo = (uint16_t)(lo > clo ? lo : clo), rhi = (uint16_t)(hi > chi ? hi : chi);
+    return (uint32_t)rlo | ((uint32_t)rhi << 16);
+#endif
+}
+BSW_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimin3_u16x2(a, b, c);
+#else
+    uint32_t lo = a & 0xffffu, hi = a >> 16;
+    if ((b & 0xffffu) < lo) lo = b & 0xffffu;
+    if ((c & 0xffffu) < lo) lo = c & 0xffffu;
+    if ((b >> 16) < hi) hi = b >> 16;
+    if ((c >> 16) < hi) hi = c >> 16;
+    return lo | (hi << 16);
+#endif
+}
+BSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh)   // ({hi,lo} >> sh) low word, 0 <= sh < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+constexpr int K1_S = TILE_LANES;            // stride (in words) between consecutive columns / words of one lane
+constexpr int K1_KEY_NONE = -1;
+
+// Score of (target row, query nibble): FAST = +match / -mismatch by nibble XOR; GENERIC = byte lookup in the
+// target base's matrix row (the RTL's 25:1 mux, sw_pe_array_mux_25to1_sel5_8_1.v:105-142).
+template <int GENERIC>
+BSW_HD int k1_score(uint32_t nib_or_xor, int mat, int mis, uint32_t rlo, uint32_t rhi)
+{
+    if (GENERIC) {
+#if defined(__CUDA_ARCH__)
+        return (int)(signed char)(__byte_perm(rlo, rhi, nib_or_xor) & 0xffu);
+#else
+        const uint64_t both = (uint64_t)rlo | ((uint64_t)rhi << 32);
+        return (int)(signed char)((both >> (8 * (nib_or_xor & 7u))) & 0xffu);
+#endif
+    }
+    return nib_or_xor ? mis : mat;
+}
+
+// One extension.  eh/qs point at this lane's column 0 / word 0 (stride K1_S); tg at this lane's target word 0
+// in the arena (stride K1_S).  eh must have qlen + 1 + K1_EH_SLACK columns, qs one zero word past the last.
+template <int VARIANT, int GENERIC, int SYM>
+BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const int h0, const int w,
+                    uint32_t* eh, const uint32_t* qs, const uint32_t* tg, SlotResult& res)
+{
+    const int o_del = P.o_del, e_del = P.e_del, e_ins = P.e_ins;
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const int zdrop = P.zdrop;
+    int mat = P.match, mis = -P.mismatch;
+    int noe_del = -oe_del, noe_ins = -oe_ins, ne_ins = -e_ins;
+    uint32_t ce_pack = 0x8000u | ((uint32_t)(-e_del) << 16);   // {-e_del, -32768}: see K1_FAST
+#if defined(__CUDA_ARCH__)
+    // keep the loop constants in ordinary registers (otherwise ptxas re-reads them from the constant bank per cell)
+    asm volatile("" : "+r"(mat), "+r"(mis), "+r"(noe_del), "+r"(noe_ins), "+r"(ne_ins), "+r"(ce_pack));
+#endif
+
+    // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
+    {
+        eh[0] = (uint32_t)h0;
+        int hv = h0 - P.o_ins;
+        for (int j = 1; j <= qlen; ++j) { hv -= e_ins; eh[j * K1_S] = (uint32_t)imax(hv, 0); }
+    }
+
+    int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;   // sx:889,1009,919,1019,1029,929
+    int beg = 0, cend = qlen;            // cend = candidate end of the coming row (qlen, then previous end + 1)
+    int resetmax = -1, stopmin = 0x7fffffff;
+    uint32_t cells = 0;
+    uint32_t tw = tg[0], tnext = 0;
+    if (tlen > 8) tnext = tg[K1_S];
+
+    for (int i = 0; i < tlen; ++i) {                                             // sx:1891
+        if ((i & 7) == 0 && i) {
+            tw = tnext;
+            if (i + 8 < tlen) tnext = tg[((i >> 3) + 1) * K1_S];                 // prefetch the next 8 rows' bases
+        }
+        const uint32_t tb = tw & 15u;
+        tw >>= 4;
+        const uint32_t trep = tb * 0x11111111u;
+        uint32_t rlo = 0, rhi = 0;
+        if (GENERIC) { rlo = P.row_lo[tb]; rhi = P.row_hi[tb]; }
+
+        int j0 = imax(beg, i - w);                                               // sx:1846,1894,1895,1803
+        int lim = imin(imin(cend, i + w + 1), qlen);                             // sx:1980,1843,1897,1898,1842
+        int fnz = 0x7fffffff, lnz = -1;                                          // V2 narrowing bookkeeping
+        if (VARIANT == 1 && stopmin < j0) {
+            // rare: the band clamp moved the start past mj+2; a zero in between ends the row (end' <= beg)
+            const int zend = imin(j0, lim);
+            for (int z = stopmin; z < zend; ++z)
+                if ((eh[z * K1_S] & 0xffffu) == 0) { lim = imin(lim, z); break; }
+        }
+        int fc;                                                                  // first column (sx:1796,1795,1880,1835,849)
+        if (VARIANT == 1 || j0 == 0) fc = imax(h0 - (o_del + e_del * (i + 1)), 0); else fc = 0;
+        if (VARIANT == 1) {
+            // trim the zero prefix (beg' = last zero + 1, sx:1766-1769) and the zero suffix (end' = first zero
+            // >= mj+2, sx:1779,1782-1789) of the candidate window; interior zeros are caught chunk by chunk.
+            while (j0 < lim && j0 <= resetmax && (eh[j0 * K1_S] & 0xffffu) == 0) ++j0;
+            while (lim > j0 && lim - 1 >= stopmin && (eh[(lim - 1) * K1_S] & 0xffffu) == 0) --lim;
+        }
+        int h1 = fc, f = 0, b_eff = j0;
+        int mkey = K1_KEY_NONE;
+        int j = j0;
+        uint32_t* ehp = eh + j * K1_S;
+
+        // One DP cell on the branch-free path.  Mirrors the RTL datapath (sw_pe_array_sw_extend.v):
+        //   M=eh.h, e=eh.e (:1799,1772) ; eh.h=h1 (:1776) ; h=M+s (:1797) ; h=max(h,e) (:1798) ; h=max(h,f) (:1809)
+        //   m/mj (:1808,1816) ; t=max(0,h-oe_del) (:1866,1862) ; e=max(e-e_del,t) (:1770-1771)
+        //   t=max(0,h-oe_ins) (:1863,1865) ; f=max(f-e_ins,t) (:1780-1781)
+        // The E update and the re-packing of {E,H} are one packed DPX op:
+        //   VIADDMNMX.S16x2({e,M} + {-e_del,-32768}, {t,h1}) = {max(e-e_del,t), h1}.
+        // The row max and its right-most column are one key (h<<16 | column) kept with a fused add-max.
+#define BSW_K1_FAST(K, W, NIB, LIVE)                                                                 \
+        {                                                                                            \
+            const int M = (int)((W) & 0xffffu), e = (int)((W) >> 16);                                \
+            const int s = k1_score<GENERIC>((NIB), mat, mis, rlo, rhi);                              \
+            const int h = imax(add_max(M, s, e), f);                                                 \
+            const int t = add_max_relu(h, noe_del, 0);                                               \
+            const uint32_t nw = add_max_s16x2((W), ce_pack, ((uint32_t)t << 16) + (uint32_t)h1);     \
+            if (SYM) f = add_max(f, ne_ins, t);                                                      \
+            else     f = add_max(f, ne_ins, add_max_relu(h, noe_ins, 0));                            \
+            if (LIVE) { ehp[(K) * K1_S] = nw; mkey = add_max(h * 65536 + j, (K), mkey); h1 = h; }    \
+        }
+#define BSW_K1_NIB(X, K) (GENERIC ? (((X) >> (4 * (K))) & 15u) : ((X) & (0xfu << (4 * (K)))))
+
+        bool stop = false;
+        while (j < lim) {
+            const int nv = lim - j;
+            const int qi = j >> 3, sh = (j & 7) * 4;
+            const uint32_t qa = funnel_r(qs[qi * K1_S], qs[(qi + 1) * K1_S], sh);
+            uint32_t x = GENERIC ? qa : (qa ^ trep);
+            if (VARIANT == 1) {
+                const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
+                const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
+                if (nv >= 8) {
+                    uint32_t zm = min3_u16x2(w0, w1, w2);
+                    zm = min3_u16x2(zm, w3, w4);
+                    zm = min3_u16x2(zm, w5, w6);
+                    zm = min3_u16x2(zm, w7, w7);
+                    if ((zm & 0xffffu) != 0) {
+                        BSW_K1_FAST(0, w0, BSW_K1_NIB(x, 0), true)
+                        BSW_K1_FAST(1, w1, BSW_K1_NIB(x, 1), true)
+                        BSW_K1_FAST(2, w2, BSW_K1_NIB(x, 2), true)
+                        BSW_K1_FAST(3, w3, BSW_K1_NIB(x, 3), true)
+                        BSW_K1_FAST(4, w4, BSW_K1_NIB(x, 4), true)
+                        BSW_K1_FAST(5, w5, BSW_K1_NIB(x, 5), true)
+                        BSW_K1_FAST(6, w6, BSW_K1_NIB(x, 6), true)
+                        BSW_K1_FAST(7, w7, BSW_K1_NIB(x, 7), true)
+                        j += 8; ehp += 8 * K1_S;
+                        continue;
+                    }
+                } else {
+                    // partial last chunk: the same code with the cells at or past lim made inert
+                    const uint32_t ones = 0xffffffffu;
+                    uint32_t zm = min3_u16x2(w0, nv > 1 ? w1 : ones, nv > 2 ? w2 : ones);
+                    zm = min3_u16x2(zm, nv > 3 ? w3 : ones, nv > 4 ? w4 : ones);
+                    zm = min3_u16x2(zm, nv > 5 ? w5 : ones, nv > 6 ? w6 : ones);
+                    if ((zm & 0xffffu) != 0) {
+                        BSW_K1_FAST(0, w0, BSW_K1_NIB(x, 0), true)
+                        BSW_K1_FAST(1, w1, BSW_K1_NIB(x, 1), nv > 1)
+                        BSW_K1_FAST(2, w2, BSW_K1_NIB(x, 2), nv > 2)
+                        BSW_K1_FAST(3, w3, BSW_K1_NIB(x, 3), nv > 3)
+                        BSW_K1_FAST(4, w4, BSW_K1_NIB(x, 4), nv > 4)
+                        BSW_K1_FAST(5, w5, BSW_K1_NIB(x, 5), nv > 5)
+                        BSW_K1_FAST(6, w6, BSW_K1_NIB(x, 6), nv > 6)
+                        j += nv; ehp += nv * K1_S;
+                        break;
+                    }
+                }
+            }
+            // careful path: cell by cell, with the narrowing events (V1) or the V2 recurrence
+            const int kmax = nv < 8 ? nv : 8;
+            for (int k = 0; k < kmax; ++k, ++j, ehp += K1_S, x >>= 4) {
+                const uint32_t wd = *ehp;
+                int M = (int)(wd & 0xffffu), e = (int)(wd >> 16);
+                if (VARIANT == 1 && M == 0) {
+                    if (j <= resetmax) { f = 0; h1 = fc; mkey = K1_KEY_NONE; b_eff = j + 1; continue; }   // beg' = j+1
+                    if (j >= stopmin) { lim = j; stop = true; break; }                                  // end' = j
+                }
+                const int s = k1_score<GENERIC>(x & 15u, mat, mis, rlo, rhi);
+                int h, g;
+                if (VARIANT == 1) { h = imax(imax(M + s, e), f); g = h; }                                // sx:1797,1798,1809
+                else { M = M ? M + s : 0; h = imax(imax(M, e), f); g = M; }                              // upstream BWA
+                mkey = imax(mkey, h * 65536 + j);                                                        // sx:1808,1816
+                int t = imax(g - oe_del, 0);                                                             // sx:1866,1862
+                e = imax(e - e_del, t);                                                                  // sx:1770-1771
+                t = imax(g - oe_ins, 0);                                                                 // sx:1863,1865
+                f = imax(f - e_ins, t);                                                                  // sx:1780-1781
+                if (VARIANT == 2) { if ((h1 | e) != 0) { lnz = j; fnz = imin(fnz, j); } }
+                *ehp = (uint32_t)h1 | ((uint32_t)e << 16);                                               // sx:1776
+                h1 = h;
+            }
+            if (stop) break;
+        }
+#undef BSW_K1_FAST
+#undef BSW_K1_NIB
+
+        const int e_eff = lim;
+        if (e_eff > b_eff) cells += (uint32_t)(e_eff - b_eff);
+        eh[e_eff * K1_S] = (uint32_t)h1;                                         // eh[end] = {h1, e=0}: sx:1775,1904
+        if (VARIANT == 2) { if (h1 != 0) lnz = e_eff; }
+        const int j_after = e_eff > b_eff ? e_eff : b_eff;                       // value of j after the reference's loop
+        if (j_after == qlen) {                                                   // sx:1768,1913
+            if (!(gscore > h1)) { max_ie = i; gscore = h1; }                     // sx:1941,1829,1831
+        }
+        int m, mj;
+        if (mkey < 0) { m = 0; mj = -1; } else { m = mkey >> 16; mj = mkey & 0xffff; }
+        if (m == 0) break;                                                       // sx:1942,1686-1687
+        if (m > max) {                                                           // sx:1959
+            max = m; max_i = i; max_j = mj;                                      // sx:1810,1833,1801
+            const int d = mj > i ? mj - i : i - mj;
+            max_off = max_off > d ? max_off : d;                                 // sx:1845,1707-1708,1964,1812
+        } else if (zdrop > 0) {                                                  // ksw_extend2 z-drop (not in the RTL)
+            const int di = i - max_i, dj = mj - max_j;
+            if (di > dj) { if (max - m - (di - dj) * e_del > zdrop) break; }
+            else         { if (max - m - (dj - di) * e_ins > zdrop) break; }
+        }
+        if (VARIANT == 1) {
+            beg = b_eff; cend = e_eff + 1; resetmax = mj; stopmin = mj + 2;      // lazy form of sx:1766-1769,1779,1782-1789
+        } else {
+            // upstream BWA: drop leading/trailing columns whose h and e are both zero
+            const int nb = fnz < e_eff ? fnz : e_eff;
+            const int jl = lnz > nb - 1 ? lnz : nb - 1;
+            beg = nb; cend = imin(jl + 2, qlen);
+        }
+    }
+    res.score = max; res.qle = max_j + 1; res.tle = max_i + 1; res.gtle = max_ie + 1;     // sx:1315-1375,1841,1868,1794
+    res.gscore = gscore; res.max_off = max_off; res.cells = (int32_t)cells; res.status = STATUS_OK;   // sx:1792,1815
+}
+
+}  // namespace bsw

@@ -1,0 +1,265 @@
+// bsw_k2.cu -- K2: intra-task extension kernel for long tasks, one warp per task (sm_100a).
+//
+// The reference caps a task at qlen <= 255 / 2048 bases (query_mem 2048x4b, eh_arr 256 entries:
+// sw_pe_array_proc_element.v:347-350, sw_pe_array_sw_extend.v:512-515); BASELINE config 4 asks for
+// 1-10 kb extensions at w=500, so this kernel has no counterpart in the RTL beyond the recurrence.
+//
+// Why not an anti-diagonal wavefront: row i+1's window [beg,end) depends on the COMPLETE row i (arg-max
+// column mj and the non-zero run around it, sw_pe_array_sw_extend.v:1766-1769,1779,1782-1789), and the
+// narrowing is not result-neutral, so a wavefront that starts row i+1 before row i ends cannot be
+// bit-exact.  K2 is row-parallel instead: a warp sweeps one row at a time in groups of 256 columns, lane l
+// owning 8 consecutive columns (two 128-bit shared-memory accesses each way).  H and E only depend on the
+// previous row.  F is a max-plus linear recurrence along the row,
+//     f[j+1] = max(f[j] - e_ins, g[j]),   g[j] = max(0, max(M[j]+s[j], e[j]) - oe_ins)
+// (g does not need f because f - oe_ins <= f - e_ins for o_ins >= 0), so each lane runs its 8 columns with
+// a zero carry-in, the carries are combined across lanes with a 5-step __shfl_up_sync prefix-max on
+// A[l] + 8*e_ins*l, and a second pass folds the carry into f/h and produces E, the row buffer, the packed
+// arg-max key and one "H == 0" bit per column.  The band narrowing is then two masked bit scans over
+// those bits (__clz/__ffs + REDUX), i.e. exactly the reference's two scan loops.
+#include <cuda_runtime.h>
+#include "bsw_device.cuh"
+#include "bsw_k1_core.cuh"
+#include "bsw_kernels.h"
+
+namespace bsw {
+
+constexpr int K2_NT = 32;
+constexpr int K2_GROUP = 256;           // columns per warp step
+constexpr int K2_HDR_BYTES = 128;
+
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// bits [a, b] (inclusive, cell indices) of the 32-cell word that starts at cell `base`
+__device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
+{
+    const int lo = imax(a - base, 0), hi = imin(b - base, 31);
+    if (lo > hi) return 0u;
+    return (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
+}
+
+template <int GENERIC>
+__global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const TileHdr hd = A.tiles[blockIdx.x];
+    const uint32_t slot = hd.slot0;
+    const SlotParam sp = A.slots[slot];
+    const int qlen = sp.qlen, tlen = sp.tlen, h0 = sp.h0, w = sp.w;
+    const int qcap = (A.qmax + 1 + K2_GROUP - 1) & ~(K2_GROUP - 1);      // row buffer columns, multiple of 256
+    const int nqw = (qlen + 7) >> 3;
+    const uint32_t qbytes = (uint32_t)((nqw * 4 + 15) & ~15);
+
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* qs = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);          // qcap/8 words (+ pad)
+    uint32_t* zb = qs + (qcap >> 3) + 4;                                          // qcap/32 words of zero bits
+    uint32_t* eh = zb + (qcap >> 5) + 4;                                          // qcap + 8 words
+    eh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(eh) + 15) & ~(uintptr_t)15);
+
+    if (lane == 0) {
+        const uint32_t bar = k2_smem_u32(mbar), dst = k2_smem_u32(qs);
+        const void* src = reinterpret_cast<const uint4*>(A.arena) + hd.qoff16;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(qbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(qbytes), "r"(bar) : "memory");
+    }
+
+    const int o_del = A.p.o_del, e_del = A.p.e_del, e_ins = A.p.e_ins;
+    const int oe_del = A.p.o_del + A.p.e_del, oe_ins = A.p.o_ins + A.p.e_ins;
+    const int zdrop = A.p.zdrop;
+    const int mat = A.p.match, mis = -A.p.mismatch;
+    const uint32_t ce_pack = 0x8000u | ((uint32_t)(-e_del) << 16);
+    const int e8 = 8 * e_ins;
+
+    // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
+    for (int j = lane; j < qcap + 8; j += K2_NT) {
+        int hv = (j == 0) ? h0 : imax(h0 - A.p.o_ins - j * e_ins, 0);
+        if (j > qlen) hv = 0;
+        eh[j] = (uint32_t)hv;
+    }
+    __syncwarp();
+    {
+        const uint32_t bar = k2_smem_u32(mbar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+    }
+
+    const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u;
+    int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;   // sx:889,1009,919,1019,1029,929
+    int beg = 0, end = qlen;                                                       // sx:769,779
+    unsigned long long cells = 0;
+    uint32_t tw = 0;
+
+    for (int i = 0; i < tlen; ++i) {                                               // sx:1891
+        if ((i & 7) == 0) tw = __ldg(tg + (i >> 3));                               // warp-uniform broadcast load
+        const uint32_t tb = (tw >> ((i & 7) * 4)) & 15u;
+        const uint32_t trep = tb * 0x11111111u;
+        uint32_t rlo = 0, rhi = 0;
+        if (GENERIC) { rlo = A.p.row_lo[tb]; rhi = A.p.row_hi[tb]; }
+
+        const int j0 = imax(beg, i - w);                                           // sx:1846,1894,1895,1803
+        const int lim = imin(imin(end, i + w + 1), qlen);                          // sx:1980,1843,1897,1898,1842
+        const int fc = imax(h0 - (o_del + e_del * (i + 1)), 0);                    // V1: unconditional (sx:1796,1795,1880,1835,849)
+        if (lim <= j0) {
+            // empty row: the reference's loop body never runs, h1 = fc, j stays at beg, m == 0 -> break
+            if (j0 == qlen) { if (!(gscore > fc)) { max_ie = i; gscore = fc; } }   // sx:1768,1913,1941
+            break;                                                                 // sx:1942
+        }
+
+        int carry = 0;            // f entering lane 0's first column of the group
+        int hcarry = fc;          // h of the column left of the group
+        int key = -1;
+        for (int gbase = j0 & ~(K2_GROUP - 1); gbase <= lim; gbase += K2_GROUP) {
+            const int jl = gbase + 8 * lane;
+            const int lo = j0 - jl, hi = lim - jl;              // columns k with lo <= k < hi are cells of this row
+            const bool full = (lo <= 0) && (hi >= 8);
+            const uint4 wa = *reinterpret_cast<const uint4*>(eh + jl);
+            const uint4 wb = *reinterpret_cast<const uint4*>(eh + jl + 4);
+            const uint32_t wd[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
+            const uint32_t qw = qs[jl >> 3];
+            const uint32_t x = GENERIC ? qw : (qw ^ trep);
+            int hh[8], fl[8];
+            int run = 0;
+            // pass 1: everything that does not need the incoming F
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
+                const int s = k1_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
+                hh[k] = add_max(M, s, e);                                          // sx:1797,1798
+                int g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
+                if (!full && !(k >= lo && k < hi)) g = 0;
+                fl[k] = run;
+                run = add_max(run, -e_ins, g);                                     // sx:1780,1781
+            }
+            // carries across lanes: prefix max of A[l] + 8*e_ins*l
+            int P = run + e8 * lane;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, P, d);
+                if (lane >= d) P = imax(P, o);
+            }
+            int Pex = __shfl_up_sync(0xffffffffu, P, 1);
+            int fin = carry - e8 * lane;
+            if (lane > 0) fin = imax(fin, Pex - e8 * (lane - 1));
+            fin = imax(fin, 0);
+            const int fout = imax(run, fin - e8);
+            carry = __shfl_sync(0xffffffffu, fout, 31);
+            // pass 2: fold the carry, finish H, E, key, zero bits
+            int h[8];
+            uint32_t enew[8];
+            uint32_t zbits = 0;
+            int u = fin;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int f = imax(fl[k], u);
+                u -= e_ins;
+                h[k] = imax(hh[k], f);                                             // sx:1809
+                const int t = add_max_relu(h[k], -oe_del, 0);                      // sx:1866,1862
+                enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);   // {max(e-e_del,t), max(M-32768,0)=0}  sx:1770-1771
+                if (full || (k >= lo && k < hi)) {
+                    key = imax(key, h[k] * 65536 + jl + k);                        // sx:1808,1816
+                    zbits |= (h[k] == 0 ? 1u : 0u) << k;
+                }
+            }
+            int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
+            if (lane == 0) hleft = hcarry;
+            hcarry = __shfl_sync(0xffffffffu, h[7], 31);
+            if (full) {
+                // interior lane: columns jl..jl+7 are all cells of this row
+                uint4 oa, ob;
+                oa.x = enew[0] | (uint32_t)((lo == 0) ? fc : hleft);
+                oa.y = enew[1] | (uint32_t)h[0]; oa.z = enew[2] | (uint32_t)h[1]; oa.w = enew[3] | (uint32_t)h[2];
+                ob.x = enew[4] | (uint32_t)h[3]; ob.y = enew[5] | (uint32_t)h[4]; ob.z = enew[6] | (uint32_t)h[5]; ob.w = enew[7] | (uint32_t)h[6];
+                *reinterpret_cast<uint4*>(eh + jl) = oa;
+                *reinterpret_cast<uint4*>(eh + jl + 4) = ob;
+            } else {
+                // boundary lane: store cells [lo,hi) and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k >= lo && k <= hi) {
+                        const int h1 = (k == lo) ? fc : (k ? h[k - 1] : hleft);
+                        eh[jl + k] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
+                    }
+                }
+            }
+            reinterpret_cast<unsigned char*>(zb)[jl >> 3] = (unsigned char)zbits;
+        }
+        __syncwarp();
+
+        // ---- row epilogue (warp-uniform) ----
+        key = __reduce_max_sync(0xffffffffu, key);
+        const int m = key >> 16, mj = key & 0xffff;
+        cells += (unsigned long long)(lim - j0);
+        const int h1 = (int)(eh[lim] & 0xffffu);
+        if (lim == qlen) {                                                         // sx:1768,1913
+            if (!(gscore > h1)) { max_ie = i; gscore = h1; }                       // sx:1941,1829,1831
+        }
+        if (m == 0) break;                                                         // sx:1942
+        if (m > max) {                                                             // sx:1959
+            max = m; max_i = i; max_j = mj;
+            const int d = mj > i ? mj - i : i - mj;
+            max_off = max_off > d ? max_off : d;                                   // sx:1707-1708,1812
+        } else if (zdrop > 0) {                                                    // ksw_extend2 z-drop (not in the RTL)
+            const int di = i - max_i, dj = mj - max_j;
+            if (di > dj) { if (max - m - (di - dj) * e_del > zdrop) break; }
+            else         { if (max - m - (dj - di) * e_ins > zdrop) break; }
+        }
+        // narrowing (sx:1766-1769 / 1779,1782-1789): zero bit of cell c <-> eh[c+1].h == 0
+        //   beg' = 2 + last zero cell in [j0, mj-1], else (fc == 0 ? j0+1 : j0)
+        //   end' = 1 + first zero cell in [mj+1, lim-1], else lim+1
+        int cb = -1, ce = 0x7fffffff;
+        for (int wbase = (j0 >> 5); wbase <= ((lim - 1) >> 5); wbase += 32) {
+            const int wi = wbase + lane;
+            const uint32_t zw = (wi <= ((lim - 1) >> 5)) ? zb[wi] : 0u;
+            const uint32_t za = zw & k2_range_mask(wi * 32, j0, mj - 1);
+            const uint32_t ze = zw & k2_range_mask(wi * 32, mj + 1, lim - 1);
+            if (za) cb = imax(cb, wi * 32 + 31 - __clz(za));
+            if (ze) ce = imin(ce, wi * 32 + __ffs(ze) - 1);
+        }
+        cb = __reduce_max_sync(0xffffffffu, cb);
+        ce = __reduce_min_sync(0xffffffffu, ce);
+        beg = cb >= 0 ? cb + 2 : (fc == 0 ? j0 + 1 : j0);
+        end = ce != 0x7fffffff ? ce + 1 : lim + 1;
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        int4* o = reinterpret_cast<int4*>(A.out + slot);
+        const unsigned long long cc = cells > 0x7fffffffull ? 0x7fffffffull : cells;
+        o[0] = make_int4(max, max_j + 1, max_i + 1, max_ie + 1);                   // sx:1315-1375 (score,qle,tle,gtle)
+        o[1] = make_int4(gscore, max_off, (int)cc, STATUS_OK);
+        if (A.cells_total && cells) atomicAdd(A.cells_total, cells);
+    }
+}
+
+size_t k2_smem_bytes(int qmax)
+{
+    const size_t qcap = ((size_t)qmax + 1 + K2_GROUP - 1) & ~(size_t)(K2_GROUP - 1);
+    return (size_t)K2_HDR_BYTES + ((qcap >> 3) + 4 + (qcap >> 5) + 4 + qcap + 8) * 4u + 16u;
+}
+
+template <int GENERIC>
+static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
+{
+    if (!a.ntiles) return cudaSuccess;
+    const size_t smem = k2_smem_bytes(a.qmax);
+    auto kern = k2_extend_kernel<GENERIC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<a.ntiles, K2_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st)
+{
+    return generic ? k2_launch_t<1>(a, st) : k2_launch_t<0>(a, st);
+}
+
+}  // namespace bsw

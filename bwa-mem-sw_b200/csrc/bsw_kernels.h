@@ -1,16 +1,21 @@
 // bsw_kernels.h -- host-callable launchers of the extension kernels.
 #pragma once
+#include <cuda_runtime.h>
 #include "bsw_device.cuh"
 
 namespace bsw {
 
-// K1: inter-task kernel (one thread per task).  variant 1|2, generic 0|1 (scoring), sym 0|1
-// (o_del==o_ins && e_del==e_ins), wide 0|1 (int32 row buffer).
-cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, int wide, cudaStream_t st);
-size_t k1_smem_bytes(int qmax, int wide);
+// K1: inter-task kernel (one lane per task, one warp-tile per CTA).  variant 1|2 (recurrence policy),
+// generic 0|1 (5x5 matrix lookup instead of match/mismatch), sym 0|1 (o_del==o_ins && e_del==e_ins).
+cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
+size_t k1_smem_bytes(int qmax, int nqw_max);
 
-// K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).
-cudaError_t k2_launch(const LaunchArgs& a, int variant, int generic, cudaStream_t st);
+// K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  Variant 1 only.
+cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st);
 size_t k2_smem_bytes(int qmax);
+
+// INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
+// streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.
+cudaError_t int_peak_run(double out_ops[5], double* sm_clock_mhz, int* sm_count, cudaStream_t st);
 
 }  // namespace bsw

@@ -1,0 +1,78 @@
+// bsw_sched.h -- host-side length-bucketed task scheduler and sequence packer.
+//
+// Plays the role of sw_pe_array_task_parse (sw_pe_array_task_parse.v:1600-1650,1652-1762: parse the
+// batch, hand every task to a PE) and of the host code that fills the task batch buffer (layout in
+// SURVEY.md App. A.1).  Pure host code, no CUDA: it is unit-tested on the CPU (tests/test_sched.py via
+// the emulation harness) and used unchanged by the product library.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "bsw_device.cuh"
+
+namespace bsw {
+
+// One extension as the scheduler sees it.  w is the band AFTER the max_ins/max_del clamp.
+struct ExtTask {
+    const uint8_t* q;
+    const uint8_t* t;
+    int32_t qlen, tlen, h0, w;
+};
+
+struct SchedOptions {
+    int variant = 1;            // 1 = RTL / BWA-0.7.8 recurrence, 2 = upstream BWA
+    int force_kernel = 0;       // 0 auto, 1 K1 only, 2 K2 only
+    int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
+    int host_threads = 0;       // 0 = hardware concurrency (capped)
+    bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
+};
+
+constexpr int K1_QLEN_CAP = 1536;        // shared-memory limit of one K1 tile (227 KB / (32 lanes * 4.5 B per column))
+constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
+constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
+
+struct Launch {
+    int kind;          // 1 = K1, 2 = K2
+    int generic;       // 1 = matrix lookup scoring
+    uint32_t tile0, ntiles;
+    int qmax, nqw_max;
+};
+
+struct Plan {
+    std::vector<TileHdr>   tiles;
+    std::vector<SlotParam> slots;
+    std::vector<int64_t>   slot_task;    // task index (into the chunk) of every slot, -1 = padding lane
+    std::vector<Launch>    launches;
+    size_t arena_words = 0;              // size of the packed sequence arena (multiple of 32 words)
+    uint64_t est_cells = 0;
+};
+
+// Per-task classification produced by validate(): bit0 = contains N (needs GENERIC), bit1 = long (K2).
+// Returns 0 or a negative BSW_E* code; on error *bad_task is the offending task and msg explains.
+int validate_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt,
+                   uint8_t* cls, size_t* bad_task, std::string* msg);
+
+// Sort, tile, bucket.  cls from validate_tasks.
+void build_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan);
+
+// Write the packed sequences of the plan into arena (plan->arena_words u32, 128-byte aligned).
+void pack_arena(const ExtTask* tasks, const Plan& plan, const SchedOptions& opt, uint32_t* arena);
+
+// ksw_extend2's band clamp (public BWA algorithm; the RTL takes max_ins/max_del precomputed from the host:
+// sw_pe_array_proc_element.v:924-934 and applies them at sw_pe_array_sw_extend.v:1763-1765,1881,1890).
+int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, int e_ins, int o_del, int e_del);
+
+// Simple fork-join helper used by the scheduler, the packer and the result scatter.
+void parallel_for(size_t n, size_t grain, int nthreads, const void* ctx,
+                  void (*fn)(const void* ctx, size_t lo, size_t hi));
+int default_host_threads();
+
+template <class F>
+inline void pfor(size_t n, size_t grain, int nthreads, F&& f)
+{
+    auto tramp = [](const void* c, size_t lo, size_t hi) { (*reinterpret_cast<const F*>(c))(lo, hi); };
+    parallel_for(n, grain, nthreads, &f, tramp);
+}
+
+}  // namespace bsw

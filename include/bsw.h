@@ -133,7 +133,9 @@ typedef struct bsw_resident bsw_resident;
 int  bsw_resident_create(bsw_ctx *ctx, const bsw_params *params,
                          const uint8_t *qbuf, const int64_t *qoff, const uint8_t *tbuf, const int64_t *toff,
                          const int32_t *h0, const int32_t *w, size_t n, bsw_resident **r);   /* pack + schedule + H2D */
-int  bsw_resident_run(bsw_ctx *ctx, bsw_resident *r);                /* kernels only; device-timed, see bsw_stats */
+/* kernels only, inputs already in HBM.  kernel_ms = CUDA-event time of the launches on their own stream,
+ * cells = DP cells evaluated (device-counted), launches = kernel launches issued; each may be NULL. */
+int  bsw_resident_run(bsw_ctx *ctx, bsw_resident *r, double *kernel_ms, uint64_t *cells, uint64_t *launches);
 int  bsw_resident_fetch(bsw_ctx *ctx, bsw_resident *r, bsw_result *out, uint32_t *cells);   /* D2H */
 void bsw_resident_free(bsw_ctx *ctx, bsw_resident *r);
 
@@ -156,6 +158,7 @@ typedef struct {
     double vimnmx_tops;        /* independent VIMNMX (max) streams */
     double dpx_tops;           /* VIADDMNMX streams, counted as 2 ops/instruction */
     double mix_tops;           /* the DP's own add/max mix (13-op cell body without memory), ops/s */
+    double dual_tops;          /* adds issued alternately as IADD3 (ALU pipe) and IMAD (FMA pipe) */
     double sm_clock_mhz;       /* clock observed during the run */
     int    sm_count;
 } bsw_int_peak;
