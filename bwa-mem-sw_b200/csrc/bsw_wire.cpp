@@ -44,7 +44,7 @@ int bsw_tbb_encode(const bsw_params2* P, const bsw_seed_task* tasks, size_t n, u
     for (size_t i = 0; i < n; ++i) {
         const bsw_seed_task& s = tasks[i];
         if (s.qlen[0] < 0 || s.qlen[0] > 255 || s.qlen[1] < 0 || s.qlen[1] > 255 || s.tlen[0] < 0 || s.tlen[0] > 2047 ||
-            s.tlen[1] < 0 || s.tlen[1] > 2047 || s.h0 < 0 || s.h0 > 255 || s.init_score < 0 || s.init_score > 65535 ||
+            s.tlen[1] < 0 || s.tlen[1] > 2047 || s.h0 < 0 || s.h0 > 255 || s.init_score < -32768 || s.init_score > 32767 ||
             s.qbeg < 0 || s.qbeg > 65535)
             return BSW_EWIRE;
         const size_t nb = (size_t)s.qlen[0] + s.qlen[1] + s.tlen[0] + s.tlen[1];
@@ -55,7 +55,7 @@ int bsw_tbb_encode(const bsw_params2* P, const bsw_seed_task* tasks, size_t n, u
         pw[0] = (uint32_t)s.qlen[0] | ((uint32_t)s.tlen[0] << 16);
         pw[1] = (uint32_t)s.qlen[1] | ((uint32_t)s.tlen[1] << 16);
         pw[2] = (uint32_t)off;
-        pw[3] = (uint32_t)s.init_score | ((uint32_t)s.qbeg << 16);
+        pw[3] = ((uint32_t)s.init_score & 0xffffu) | ((uint32_t)s.qbeg << 16);
         pw[4] = (uint32_t)s.h0;
         for (int side = 0; side < 2; ++side) {
             // the host precomputes ksw_extend2's max_ins / max_del (end_bonus = pen_clip5 / pen_clip3)
@@ -135,7 +135,7 @@ int bsw_fpga_batch(bsw_ctx* ctx, const uint32_t* tbb, uint32_t* rbb, int* n_resu
         bsw_seed_task& s = tasks[i];
         s.qlen[0] = (int)(pw[0] & 0xff); s.tlen[0] = (int)((pw[0] >> 16) & 0x7ff);   // proc_element.v:880-883
         s.qlen[1] = (int)(pw[1] & 0xff); s.tlen[1] = (int)((pw[1] >> 16) & 0x7ff);   // proc_element.v:889-892
-        s.init_score = (int)(pw[3] & 0xffff); s.qbeg = (int)(pw[3] >> 16);           // proc_element.v:871-874
+        s.init_score = (int16_t)(pw[3] & 0xffff); s.qbeg = (int)(pw[3] >> 16);   // regScore is BWA's a->score before the task (-1 = unset)           // proc_element.v:871-874
         s.h0 = (int)(pw[4] & 0xff);                                                  // proc_element.v:826-828
         clamps[i].max_ins[0] = (int)(pw[5] & 0xffff); clamps[i].max_del[0] = (int)(pw[5] >> 16);   // proc_element.v:924-926
         clamps[i].max_ins[1] = (int)(pw[6] & 0xffff); clamps[i].max_del[1] = (int)(pw[6] >> 16);   // proc_element.v:932-934

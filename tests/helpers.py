@@ -1,0 +1,54 @@
+"""Shared test helpers: seed-task construction and comparisons (test infrastructure)."""
+import numpy as np
+
+
+def flat_from_lists(queries, targets):
+    qoff = np.zeros(len(queries) + 1, dtype=np.int64)
+    toff = np.zeros(len(targets) + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in queries], out=qoff[1:])
+    np.cumsum([len(t) for t in targets], out=toff[1:])
+    qbuf = np.concatenate([np.asarray(q, dtype=np.uint8) for q in queries] + [np.zeros(8, np.uint8)])
+    tbuf = np.concatenate([np.asarray(t, dtype=np.uint8) for t in targets] + [np.zeros(8, np.uint8)])
+    return qbuf, qoff, tbuf, toff
+
+
+def seeds_from_flat(t, n_reads, unset_score_every=0):
+    """Pair flat tasks (2r = reversed left flank, 2r+1 = right flank) into level-2 seed tasks."""
+    seeds = []
+    for r in range(n_reads):
+        l, g = 2 * r, 2 * r + 1
+        ql = t["qbuf"][t["qoff"][l]:t["qoff"][l + 1]]
+        tl = t["tbuf"][t["toff"][l]:t["toff"][l + 1]]
+        qr = t["qbuf"][t["qoff"][g]:t["qoff"][g + 1]]
+        tr = t["tbuf"][t["toff"][g]:t["toff"][g + 1]]
+        h0 = int(t["h0"][l])
+        kind = r % 4
+        if kind == 1:      # no left flank: BWA sets a->score = seed_len*a and skips the left extension
+            ql, tl = ql[:0], tl[:0]
+        elif kind == 2:    # no right flank
+            qr, tr = qr[:0], tr[:0]
+        init = h0 if (len(ql) == 0 or not unset_score_every or r % unset_score_every) else -1
+        seeds.append(dict(q_left=ql, q_right=qr, t_left=tl, t_right=tr, init_score=init, qbeg=len(ql), h0=h0, id=1000 + r))
+    return seeds
+
+
+def assert_same(a, b, what=""):
+    bad = np.nonzero(a != b)[0]
+    assert len(bad) == 0, f"{what}: {len(bad)} mismatches, first at {bad[0]}: {a[bad[0]]} vs {b[bad[0]]}"
+
+
+def oracle_params(O, p):
+    """Byte-copy a bsw_b200.Params / Params2 into the oracle's own ctypes class of the same layout."""
+    import ctypes as C
+    cls = O.Params2 if hasattr(p, "pen_clip5") else O.Params
+    q = cls()
+    assert C.sizeof(q) == C.sizeof(p)
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(p))
+    return q
+
+
+def oracle_chain2aln(O, B, params2, seeds, variant=1):
+    tasks, keep = B.make_seed_tasks(seeds)
+    out, cells = O.chain2aln_batch(oracle_params(O, params2), tasks, variant=variant)
+    del keep
+    return out, cells

@@ -1,0 +1,223 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libbsw.so), against the CPU oracle on the same
+seeded inputs and against the frozen golden vectors.  All outputs are integers: the bar is bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, flat_from_lists, oracle_chain2aln, seeds_from_flat
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+L1 = sorted(glob.glob(os.path.join(GOLD, "l1_*.npz")))
+
+
+def both(B, O, ctx, t, variant=1, opts=None, **pk):
+    p, po = B.make_params(**pk), O.make_params(**pk)
+    ctx.set_option("variant", variant)
+    for k, v in (opts or {}).items():
+        ctx.set_option(k, v)
+    try:
+        ro, co = O.extend_batch(po, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"], variant=variant)
+        rg, cg = ctx.sw_extend_batch(p, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    finally:
+        ctx.set_option("variant", 1); ctx.set_option("force_kernel", 0); ctx.set_option("k2_min_qlen", 384)
+    assert_same(ro, rg, "results")
+    assert_same(co.astype(np.int64), cg.astype(np.int64), "cells")
+    return ro, co
+
+
+def test_native_library_is_loaded(B, ctx):
+    maps = open("/proc/self/maps").read()
+    assert "libbsw.so" in maps
+    assert ctx.num_devices >= 1
+
+
+@pytest.mark.parametrize("name,n", [("cfg1_101bp", 100_000), ("cfg2_150bp", 60_000), ("cfg3_mixed", 60_000)])
+def test_k1_workloads(B, O, ctx, name, n):
+    both(B, O, ctx, B.synth_tasks(name, n, seed=2))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_k1_variants_with_ambiguous_bases(B, O, ctx, variant):
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 20_000, seed=3, n_frac=0.01), variant=variant)
+
+
+@pytest.mark.parametrize("pk", [dict(o_del=4, e_del=2, o_ins=7, e_ins=1), dict(a=2, b=3, zdrop=20),
+                                dict(zdrop=0, o_del=0, o_ins=0), dict(o_del=0, e_del=3, o_ins=9, e_ins=2, end_bonus=0)])
+def test_k1_scoring_variations(B, O, ctx, pk):
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=4), **pk)
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=4), variant=2, **pk)
+
+
+def test_custom_matrix(B, O, ctx):
+    m = B.bwa_fill_scmat(1, 4).copy()
+    m[1], m[7], m[24] = 2, -3, 0
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=5), mat=m)
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 3_000, seed=5), mat=m, opts={"force_kernel": 2})
+
+
+def test_k2_on_short_tasks(B, O, ctx):
+    """The intra-task kernel forced onto short/mixed tasks: same answers as K1 and the oracle."""
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=6), opts={"force_kernel": 2})
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=6, n_frac=0.02), opts={"force_kernel": 2})
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=7), opts={"force_kernel": 2}, o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30)
+
+
+def test_k2_long_reads(B, O, ctx):
+    """BASELINE config 4: 1-10 kb, w=500, PacBio-like errors (zdrop 100 and 400)."""
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 96, seed=8))
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 48, seed=9), zdrop=400)
+
+
+def test_mixed_short_and_long_in_one_batch(B, O, ctx):
+    a, b = B.synth_tasks("cfg3_mixed", 3000, seed=10), B.synth_tasks("cfg4_long", 8, seed=10)
+    t = dict(qbuf=np.concatenate([a["qbuf"][:a["qoff"][-1]], b["qbuf"]]), tbuf=np.concatenate([a["tbuf"][:a["toff"][-1]], b["tbuf"]]),
+             qoff=np.concatenate([a["qoff"], b["qoff"][1:] + a["qoff"][-1]]), toff=np.concatenate([a["toff"], b["toff"][1:] + a["toff"][-1]]),
+             h0=np.concatenate([a["h0"], b["h0"]]), w=np.concatenate([a["w"], b["w"]]))
+    both(B, O, ctx, t)
+    both(B, O, ctx, t, opts={"k2_min_qlen": 100})
+
+
+def test_edge_shapes(B, O, ctx):
+    rng = np.random.default_rng(9)
+    qs, ts, h0, w = [], [], [], []
+    for qlen, tlen, h, ww in [(1, 1, 1, 100), (1, 50, 30, 100), (50, 1, 30, 100), (8, 8, 5, 0), (9, 200, 100, 3),
+                              (16, 16, 1, 100), (17, 40, 300, 1), (255, 600, 19, 100), (300, 310, 1000, 50),
+                              (256, 256, 20, 100), (257, 513, 20, 100), (1536, 1600, 50, 100), (1537, 1600, 50, 100)]:
+        q = rng.integers(0, 4, qlen).astype(np.uint8)
+        t = np.resize(q, tlen).astype(np.uint8)
+        t[rng.random(tlen) < 0.1] = 3
+        qs.append(q); ts.append(t); h0.append(h); w.append(ww)
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
+    both(B, O, ctx, t)
+    both(B, O, ctx, t, opts={"force_kernel": 2})
+    t2 = {k: (v[:-1] if k in ("h0", "w") else v) for k, v in t.items()}
+    t2["qoff"], t2["toff"] = t["qoff"][:-1], t["toff"][:-1]        # drop the 1537-long task: V2 is K1-only
+    both(B, O, ctx, t2, variant=2)
+
+
+def test_empty_batch_and_errors(B, ctx):
+    p = B.make_params()
+    out, _ = ctx.sw_extend_batch(p, np.zeros(8, np.uint8), np.zeros(1, np.int64), np.zeros(8, np.uint8), np.zeros(1, np.int64),
+                                 np.zeros(0, np.int32), np.zeros(0, np.int32))
+    assert len(out) == 0
+    q = np.array([0, 1, 9, 2], np.uint8)
+    qbuf, qoff, tbuf, toff = flat_from_lists([q], [q])
+    with pytest.raises(B.BswError) as e:
+        ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [10], [100])
+    assert e.value.code == B.BSW_EINVAL and "task 0" in str(e.value)
+    good = np.array([0, 1, 2, 3], np.uint8)
+    qbuf, qoff, tbuf, toff = flat_from_lists([good], [good])
+    with pytest.raises(B.BswError) as e:                     # h0 must be > 0 (sw_extend precondition)
+        ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [0], [100])
+    assert e.value.code == B.BSW_EINVAL
+    with pytest.raises(B.BswError) as e:                     # 16-bit row-state envelope
+        ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [40000], [100])
+    assert e.value.code == B.BSW_ERANGE
+    bad = B.make_params(e_del=0)
+    with pytest.raises(B.BswError):
+        ctx.sw_extend_batch(bad, qbuf, qoff, tbuf, toff, [10], [100])
+
+
+def test_task_record_layout_and_async(B, O, ctx):
+    t = B.synth_tasks("cfg3_mixed", 500, seed=12)
+    qs = [t["qbuf"][t["qoff"][i]:t["qoff"][i + 1]] for i in range(500)]
+    ts = [t["tbuf"][t["toff"][i]:t["toff"][i + 1]] for i in range(500)]
+    p, po = B.make_params(), O.make_params()
+    ro, _ = O.extend_batch(po, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    assert_same(ro, ctx.sw_extend_tasks(p, qs, ts, t["h0"], t["w"]), "bsw_extend_batch")
+    # async pair: submit / poll / wait (the FPGA's "write REQ_PEARRAY, poll the DSM busy bit")
+    import ctypes as C
+    qa = [np.ascontiguousarray(q) for q in qs]; ta = [np.ascontiguousarray(x) for x in ts]
+    tasks = (B.Task * 500)()
+    for i in range(500):
+        tasks[i].query, tasks[i].target = qa[i].ctypes.data, ta[i].ctypes.data
+        tasks[i].qlen, tasks[i].tlen, tasks[i].h0, tasks[i].w = len(qa[i]), len(ta[i]), int(t["h0"][i]), int(t["w"][i])
+    out = np.zeros(500, dtype=B.RESULT_DTYPE)
+    tk = ctx.submit(p, tasks, 500, out)
+    ctx.wait(tk)
+    assert_same(ro, out, "async")
+
+
+@pytest.mark.parametrize("path", L1, ids=[os.path.basename(p) for p in L1])
+def test_golden_level1(B, ctx, path):
+    g = np.load(path)
+    s = g["scal"]
+    p = B.make_params(mat=g["mat"], o_del=int(s[0]), e_del=int(s[1]), o_ins=int(s[2]), e_ins=int(s[3]), zdrop=int(s[4]), end_bonus=int(s[5]))
+    ctx.set_option("variant", int(s[6]))
+    try:
+        res, cells = ctx.sw_extend_batch(p, g["qbuf"], g["qoff"], g["tbuf"], g["toff"], g["h0"], g["w"])
+    finally:
+        ctx.set_option("variant", 1)
+    assert_same(res, g["res"], "CUDA vs golden")
+    assert_same(cells.astype(np.int64), g["cells"], "cells")
+
+
+def test_golden_level2(B, ctx):
+    g = np.load(os.path.join(GOLD, "l2_cfg3.npz"))
+    seeds = seeds_from_flat(g, int(g["nreads"]), unset_score_every=3)
+    got = ctx.proc_element_batch(B.make_params2(w=100, pen_clip5=5, pen_clip3=5), seeds)
+    assert_same(got, g["rec"], "level 2 vs golden")
+
+
+@pytest.mark.parametrize("w,zdrop", [(100, 100), (10, 100), (5, 0)])
+def test_level2_proc_element(B, O, ctx, w, zdrop):
+    """left + right extension, band-doubling retry (small w forces the second try), clip decision."""
+    t = B.synth_tasks("cfg3_mixed", 4000, seed=20 + w)
+    seeds = seeds_from_flat(t, 2000, unset_score_every=3)
+    P2 = B.make_params2(B.make_params(zdrop=zdrop), w=w, pen_clip5=5, pen_clip3=7)
+    want, _ = oracle_chain2aln(O, B, P2, seeds)
+    got = ctx.proc_element_batch(P2, seeds)
+    assert_same(want, got, "proc_element")
+    if w < 100:
+        assert (want["w"] == 2 * w).any()          # the retry path ran
+
+
+def test_level3_wire_format(B, O, ctx):
+    """TBB image in, RBB image out (the FPGA has no z-drop and a fixed +1/-4/-1 matrix: compare with zdrop=0)."""
+    t = B.synth_tasks("cfg1_101bp", 1600, seed=30)
+    seeds = seeds_from_flat(t, 800, unset_score_every=4)
+    P2 = B.make_params2(B.make_params(zdrop=0), w=100, pen_clip5=5, pen_clip3=5)
+    want, _ = oracle_chain2aln(O, B, P2, seeds)
+    tbb = B.tbb_encode(P2, seeds)
+    rbb, n = ctx.pe_array_batch(tbb)
+    assert n == 800
+    got = B.rbb_decode(rbb, n)
+    assert_same(want, got, "RBB records")
+    assert not rbb[5 * n:].any()                   # words past the records are left untouched
+
+
+def test_full_size_properties(B, O, ctx):
+    """BASELINE configs[1] at full size (1M x 150 bp): size-independent properties + a 1% oracle sample."""
+    n = 1_000_000
+    t = B.synth_tasks("cfg2_150bp", n, seed=1)
+    p, po = B.make_params(), O.make_params()
+    ctx.reset_stats()
+    r, c = ctx.sw_extend_batch(p, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    st = ctx.stats()
+    qlen = np.diff(t["qoff"]); tlen = np.diff(t["toff"])
+    assert st["tasks"] == n and st["cells_band"] == int(c.astype(np.int64).sum())       # device counter == sum of per-task cells
+    assert (r["score"] >= t["h0"]).all() and (r["score"] <= t["h0"] + qlen).all()
+    assert (r["qle"] >= 0).all() and (r["qle"] <= qlen).all() and (r["tle"] >= 0).all() and (r["tle"] <= tlen).all()
+    assert (r["gtle"] <= tlen).all() and (r["gscore"] <= r["score"]).all() and (r["max_off"] >= 0).all()
+    assert (c <= qlen.astype(np.int64) * tlen).all()
+    # idempotence + permutation invariance (the scheduler reorders tasks internally)
+    perm = np.random.default_rng(0).permutation(n)[:50_000]
+    qs = np.concatenate([[0], np.cumsum(qlen[perm])]); ts = np.concatenate([[0], np.cumsum(tlen[perm])])
+    qb = np.concatenate([t["qbuf"][t["qoff"][i]:t["qoff"][i + 1]] for i in perm] + [np.zeros(8, np.uint8)])
+    tb = np.concatenate([t["tbuf"][t["toff"][i]:t["toff"][i + 1]] for i in perm] + [np.zeros(8, np.uint8)])
+    r2, c2 = ctx.sw_extend_batch(p, qb, qs, tb, ts, t["h0"][perm], t["w"][perm])
+    assert_same(r[perm], r2, "permutation invariance")
+    assert_same(c[perm], c2, "cells under permutation")
+    # oracle on the permuted 5% sample
+    ro, co = O.extend_batch(po, qb, qs, tb, ts, t["h0"][perm], t["w"][perm])
+    assert_same(ro, r2, "oracle sample")
+    assert_same(co, c2.astype(np.int64), "oracle sample cells")
+
+
+def test_int_peak_microbenchmark(ctx):
+    pk = ctx.measure_int_peak(0)
+    assert pk["sm_count"] >= 100 and 5.0 < pk["iadd_tops"] < 80.0 and pk["dpx_tops"] > pk["vimnmx_tops"]
