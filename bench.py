@@ -193,13 +193,14 @@ def main():
     res.free()
 
     # ---------------- e2e: public C-ABI call with host buffers ----------------
+    out_buf = np.zeros(n, dtype=B.RESULT_DTYPE)                     # caller-owned result array, as a C caller would hold
     for _ in range(max(args.warmup, 3)):
-        ctx.sw_extend_batch(p, *flat, want_cells=False)
+        ctx.sw_extend_batch(p, *flat, want_cells=False, out=out_buf)
     ctx.reset_stats()
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.sw_extend_batch(p, *flat, want_cells=False)
+        ctx.sw_extend_batch(p, *flat, want_cells=False, out=out_buf)
     barrier()
     e2e_s = time.perf_counter() - e0
     st = ctx.stats()

@@ -236,11 +236,15 @@ class Context:
         return lib().bsw_num_devices(self.handle)
 
     # ---- level 1: sw_extend ----
-    def sw_extend_batch(self, params: Params, qbuf, qoff, tbuf, toff, h0, w, want_cells: bool = True):
-        """Flat layout: task i's query is qbuf[qoff[i]:qoff[i+1]].  Returns (results[RESULT_DTYPE], cells[uint32])."""
+    def sw_extend_batch(self, params: Params, qbuf, qoff, tbuf, toff, h0, w, want_cells: bool = True, out=None, cells=None):
+        """Flat layout: task i's query is qbuf[qoff[i]:qoff[i+1]].  Returns (results[RESULT_DTYPE], cells[uint32]).
+        out / cells: optional caller-owned result arrays (the C ABI writes into caller buffers; reuse them across calls)."""
         qbuf, qoff, tbuf, toff, h0, w, n = _flat_args(qbuf, qoff, tbuf, toff, h0, w)
-        out = np.zeros(n, dtype=RESULT_DTYPE)
-        cells = np.zeros(n, dtype=np.uint32)
+        if out is None:
+            out = np.zeros(n, dtype=RESULT_DTYPE)
+        if cells is None:
+            cells = np.zeros(n if want_cells else 0, dtype=np.uint32)
+        assert out.dtype == RESULT_DTYPE and len(out) == n and out.flags.c_contiguous
         self._check(lib().bsw_extend_batch_flat(self.handle, C.byref(params), qbuf.ctypes.data, qoff.ctypes.data,
                                                 tbuf.ctypes.data, toff.ctypes.data, h0.ctypes.data, w.ctypes.data, n,
                                                 out.ctypes.data, cells.ctypes.data if want_cells else None))

@@ -33,6 +33,10 @@ struct __attribute__((aligned(16))) TileHdr {
 
 struct __attribute__((aligned(16))) SlotParam { int32_t qlen, tlen, h0, w; };   // qlen == 0: padding lane
 
+// Where a slot's packed query / target live in the task-major SOURCE arena (16-byte units).  The host packs every
+// sequence once, in input order (a streaming pass); the k0 gather kernel re-lays K1 tiles on the device.
+struct SlotSrc { uint32_t qoff16, toff16; };
+
 struct __attribute__((aligned(16))) SlotResult {       // two 16-byte stores per task
     int32_t score, qle, tle, gtle;                      // sw_extend return order (sw_pe_array_sw_extend.v:117-123)
     int32_t gscore, max_off, cells, status;
@@ -46,11 +50,21 @@ struct DevParams {
     int8_t  mat[28];               // the 5x5 matrix itself (K2 GENERIC lookup), padded
 };
 
+// k0: gather launch = K1 tiles [0, ntiles) of `tiles`; copies src words of every lane into the tiled arena.
+struct GatherArgs {
+    const TileHdr*   tiles;
+    const SlotParam* slots;
+    const SlotSrc*   slot_src;
+    const uint32_t*  src;          // task-major source arena (H2D copy of the host packer's output)
+    uint32_t*        dst;          // tiled arena
+    uint32_t         ntiles;
+};
+
 // One kernel launch = tiles [0, ntiles) of `tiles`.
 struct LaunchArgs {
     const TileHdr*   tiles;
     const SlotParam* slots;
-    const uint32_t*  arena;        // packed sequences, 16-byte aligned blocks
+    const uint32_t*  arena;        // K1: tiled arena; K2: source arena (16-byte aligned blocks)
     SlotResult*      out;          // indexed by slot
     unsigned long long* cells_total;   // device counter of evaluated DP cells (one atomic per warp), may be null
     DevParams        p;

@@ -39,36 +39,60 @@ double now_ms()
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
-    // pinned host staging
-    uint32_t* h_arena = nullptr;  size_t h_arena_cap = 0;
-    TileHdr* h_tiles = nullptr;   size_t h_tiles_cap = 0;
-    SlotParam* h_slots = nullptr; size_t h_slots_cap = 0;
+    // One pinned input block per chunk, mirrored on the device and moved with a single cudaMemcpyAsync:
+    //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] ]   (16-byte aligned parts)
+    unsigned char* h_in = nullptr; size_t h_in_cap = 0;
+    unsigned char* d_in = nullptr; size_t d_in_cap = 0;
+    size_t in_bytes = 0, off_tiles = 0, off_slots = 0, off_ssrc = 0;
     SlotResult* h_out = nullptr;  size_t h_out_cap = 0;
-    // device
-    uint32_t* d_arena = nullptr;  size_t d_arena_cap = 0;
-    TileHdr* d_tiles = nullptr;   size_t d_tiles_cap = 0;
-    SlotParam* d_slots = nullptr; size_t d_slots_cap = 0;
+    uint32_t* d_arena = nullptr;  size_t d_arena_cap = 0;     // tiled arena, written by the k0 gather kernel
     SlotResult* d_out = nullptr;  size_t d_out_cap = 0;
+    size_t src_words = 0;
+    const uint32_t*  d_src() const { return reinterpret_cast<const uint32_t*>(d_in); }
+    const TileHdr*   d_tiles() const { return reinterpret_cast<const TileHdr*>(d_in + off_tiles); }
+    const SlotParam* d_slots() const { return reinterpret_cast<const SlotParam*>(d_in + off_slots); }
+    const SlotSrc*   d_ssrc() const { return reinterpret_cast<const SlotSrc*>(d_in + off_ssrc); }
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
     // in-flight bookkeeping
-    bool busy = false;
+    bool busy = false, timed = false;
     Plan plan;
     size_t first = 0, count = 0;     // chunk = tasks [first, first+count) of the batch
     size_t nlaunch = 0;
+    // per-chunk host scratch (reused)
+    std::vector<ExtTask> tasks;
+    std::vector<uint8_t> cls;
+    std::vector<SlotSrc> src;
+};
+
+// One host worker thread = one pipeline: it owns two staging slots (streams) on one device and alternates between
+// them, so the chunk it packs overlaps the chunk the GPU is computing.
+struct Worker {
+    int dev = 0;
+    bool ready = false;
+    Slot slots[2];
 };
 
 struct Device {
     int id = 0;
-    std::vector<Slot> slots;
+    Slot aux;                        // stream for measurement kernels
+};
+
+// Where a batch's tasks come from (flat arrays, bsw_task records, or an internal ExtTask vector).
+struct TaskSource {
+    const void* self;
+    void (*fill)(const void* self, size_t first, size_t count, ExtTask* out);
 };
 
 }  // namespace
 
 struct bsw_ctx {
     std::vector<Device> devs;
+    std::vector<std::unique_ptr<Worker>> workers;
+    int streams_per_device = 2;
     SchedOptions opt;
-    size_t chunk_tasks = 262144;
+    size_t chunk_tasks = 32768;
+    bool kernel_timing = true;     // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms)
     std::mutex mu;                 // serialises batch calls on this context
     std::mutex err_mu;
     std::string last_error;
@@ -83,7 +107,7 @@ struct bsw_resident {
     int dev = 0;
     Slot slot;
     DevParams dp{};
-    int sym = 0;
+    int sym = 0, variant = 1;
     size_t n = 0;
     double last_ms = 0;
 };
@@ -137,7 +161,7 @@ int slot_init(bsw_ctx* ctx, Slot& s)
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k0));
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k1));
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_TRY(ctx, cudaMalloc((void**)&s.d_cells, sizeof(unsigned long long)));
     CUDA_TRY(ctx, cudaHostAlloc((void**)&s.h_cells, sizeof(unsigned long long), cudaHostAllocDefault));
     return 0;
@@ -145,14 +169,11 @@ int slot_init(bsw_ctx* ctx, Slot& s)
 
 void slot_free(Slot& s)
 {
-    if (s.h_arena) cudaFreeHost(s.h_arena);
-    if (s.h_tiles) cudaFreeHost(s.h_tiles);
-    if (s.h_slots) cudaFreeHost(s.h_slots);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.d_in) cudaFree(s.d_in);
     if (s.h_out) cudaFreeHost(s.h_out);
     if (s.h_cells) cudaFreeHost(s.h_cells);
     if (s.d_arena) cudaFree(s.d_arena);
-    if (s.d_tiles) cudaFree(s.d_tiles);
-    if (s.d_slots) cudaFree(s.d_slots);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_cells) cudaFree(s.d_cells);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -193,95 +214,142 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
     return 0;
 }
 
-// Schedule + pack tasks [first, first+count) into the slot's pinned staging, then enqueue H2D, kernels and D2H.
-int slot_submit(bsw_ctx* ctx, Slot& s, const ExtTask* tasks, const uint8_t* cls, size_t first, size_t count,
-                const DevParams& dp, int sym, const SchedOptions& opt, bool timing)
-{
-    const double t0 = now_ms();
-    build_plan(tasks + first, cls + first, count, opt, &s.plan);
-    Plan& P = s.plan;
-    int rc;
-    if ((rc = grow_pinned(ctx, &s.h_arena, &s.h_arena_cap, P.arena_words))) return rc;
-    if ((rc = grow_pinned(ctx, &s.h_tiles, &s.h_tiles_cap, P.tiles.size()))) return rc;
-    if ((rc = grow_pinned(ctx, &s.h_slots, &s.h_slots_cap, P.slots.size()))) return rc;
-    if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, P.slots.size()))) return rc;
-    if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.arena_words))) return rc;
-    if ((rc = grow_device(ctx, &s.d_tiles, &s.d_tiles_cap, P.tiles.size()))) return rc;
-    if ((rc = grow_device(ctx, &s.d_slots, &s.d_slots_cap, P.slots.size()))) return rc;
-    if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, P.slots.size()))) return rc;
-    pack_arena(tasks + first, P, opt, s.h_arena);
-    memcpy(s.h_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
-    memcpy(s.h_slots, P.slots.data(), P.slots.size() * sizeof(SlotParam));
-    const double t1 = now_ms();
+// Host statistics accumulated by one worker and merged once per call.
+struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0; };
 
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_arena, s.h_arena, P.arena_words * 4, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_tiles, s.h_tiles, P.tiles.size() * sizeof(TileHdr), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_slots, s.h_slots, P.slots.size() * sizeof(SlotParam), cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
-    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
-    s.nlaunch = 0;
+int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch)
+{
+    const Plan& P = s.plan;
+    size_t nl = 0;
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
-        a.tiles = s.d_tiles + L.tile0; a.slots = s.d_slots; a.arena = s.d_arena; a.out = s.d_out;
-        a.cells_total = s.d_cells; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
-        cudaError_t e = (L.kind == 1) ? k1_launch(a, opt.variant, L.generic, sym, s.stream)
+        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 1) ? s.d_arena : s.d_src(); a.out = s.d_out;
+        a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+        cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, s.stream)
                                       : k2_launch(a, L.generic, s.stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : "K2 launch");
-        ++s.nlaunch;
+        ++nl;
     }
+    *nlaunch = nl;
+    return 0;
+}
+
+int enqueue_gather(bsw_ctx* ctx, Slot& s)
+{
+    const Plan& P = s.plan;
+    if (!P.n_k1_tiles) return 0;
+    GatherArgs g{};
+    g.tiles = s.d_tiles(); g.slots = s.d_slots(); g.slot_src = s.d_ssrc(); g.src = s.d_src(); g.dst = s.d_arena; g.ntiles = P.n_k1_tiles;
+    cudaError_t e = k0_launch(g, s.stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "K0 gather launch");
+    return 0;
+}
+
+// Pack + schedule the chunk held in s.tasks (tasks [first, first+count) of the batch) into the slot's pinned staging,
+// then enqueue H2D, the k0 gather, the extension kernels and D2H on the slot's stream.
+int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, const DevParams& dp, int sym,
+                const SchedOptions& opt, bool timing, LocalStats* st)
+{
+    const double t0 = now_ms();
+    int rc;
+    // upper bounds of the input block: nslots <= count + 4 classes * 31 padding lanes, tiles <= count + 4
+    const size_t src_bound = source_arena_bound(s.tasks.data(), count) * 4;
+    const size_t max_slots = count + 4 * TILE_LANES, max_tiles = count + 4;
+    const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc)) + 64;
+    if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bound))) return rc;
+    s.cls.resize(count); s.src.resize(count);
+    size_t bad = 0; std::string msg;
+    rc = pack_tasks(s.tasks.data(), count, max_mat, opt, s.cls.data(), s.src.data(), reinterpret_cast<uint32_t*>(s.h_in),
+                    &s.src_words, &bad, &msg);
+    if (rc) {
+        const size_t colon = msg.find(':');
+        set_error(ctx, "task " + std::to_string(first + bad) + (colon == std::string::npos ? "" : msg.substr(colon)));
+        return rc;
+    }
+    const double t1 = now_ms();
+    build_plan(s.tasks.data(), s.cls.data(), s.src.data(), count, opt, &s.plan);
+    Plan& P = s.plan;
+    const size_t nslots = P.slots.size();
+    s.off_tiles = (s.src_words * 4 + 15) & ~(size_t)15;
+    s.off_slots = s.off_tiles + P.tiles.size() * sizeof(TileHdr);
+    s.off_ssrc = s.off_slots + nslots * sizeof(SlotParam);
+    s.in_bytes = s.off_ssrc + nslots * sizeof(SlotSrc);
+    if (s.in_bytes > s.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); return BSW_ENOMEM; }
+    if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, nslots))) return rc;
+    if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
+    if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.tiled_words))) return rc;
+    if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, nslots))) return rc;
+    memcpy(s.h_in + s.off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
+    memcpy(s.h_in + s.off_slots, P.slots.data(), nslots * sizeof(SlotParam));
+    memcpy(s.h_in + s.off_ssrc, P.slot_src.data(), nslots * sizeof(SlotSrc));
+    const double t2 = now_ms();
+
+    // per chunk: 1 H2D, 1 gather, the bucket launches, 1 D2H, 1 event (the per-task cells come back in the records)
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    if ((rc = enqueue_gather(ctx, s))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch))) return rc;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, P.slots.size() * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, nslots * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
+    s.timed = timing;
     s.busy = true; s.first = first; s.count = count;
-    {
-        std::lock_guard<std::mutex> g(ctx->err_mu);
-        ctx->stats.pack_ms += t1 - t0;
-        ctx->stats.h2d_bytes += P.arena_words * 4 + P.tiles.size() * sizeof(TileHdr) + P.slots.size() * sizeof(SlotParam);
-        ctx->stats.d2h_bytes += P.slots.size() * sizeof(SlotResult) + 8;
-        ctx->stats.kernel_launches += s.nlaunch;
-    }
+    if (P.n_k1_tiles) ++s.nlaunch;
+    st->validate_ms += t1 - t0;
+    st->pack_ms += t2 - t1;
+    st->h2d += s.in_bytes;
+    st->d2h += nslots * sizeof(SlotResult);
+    st->launches += s.nlaunch;
     return 0;
 }
 
 // Wait for the slot's chunk and scatter its results to out[first + task].
-int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, const SchedOptions& opt, bool timing)
+int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st)
 {
     if (!s.busy) return 0;
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
     s.busy = false;
     float ms = 0.f;
-    if (timing) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    if (s.timed) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     const Plan& P = s.plan;
     const size_t nslots = P.slots.size();
     const size_t first = s.first;
     const SlotResult* h_out = s.h_out;
-    std::atomic<int> bad(0);
-    pfor(nslots, 8192, opt.host_threads, [&](size_t lo, size_t hi) {
-        for (size_t k = lo; k < hi; ++k) {
-            const int64_t t = P.slot_task[k];
-            if (t < 0) continue;
-            const SlotResult& r = h_out[k];
-            if (r.status != STATUS_OK) bad.store(1);
-            bsw_result& o = out[first + (size_t)t];
-            o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
-            if (cells) cells[first + (size_t)t] = (uint32_t)r.cells;
-        }
-    });
-    {
-        std::lock_guard<std::mutex> g(ctx->err_mu);
-        ctx->stats.tasks += s.count;
-        ctx->stats.cells_band += *s.h_cells;
-        ctx->stats.kernel_ms += ms;
+    int bad = 0;
+    uint64_t cell_sum = 0;
+    for (size_t k = 0; k < nslots; ++k) {
+        const int64_t t = P.slot_task[k];
+        if (t < 0) continue;
+        const SlotResult& r = h_out[k];
+        if (r.status != STATUS_OK) bad = 1;
+        cell_sum += (uint32_t)r.cells;
+        bsw_result& o = out[first + (size_t)t];
+        o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
+        if (cells) cells[first + (size_t)t] = (uint32_t)r.cells;
     }
-    if (bad.load()) { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
+    st->tasks += s.count; st->cells += cell_sum; st->kernel_ms += ms;
+    if (bad) { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
     return 0;
 }
 
-// The engine behind every batch entry point: validate, shard over devices, pipeline chunks over stream slots.
-int run_extensions(bsw_ctx* ctx, const bsw_params* params, const ExtTask* tasks, size_t n, bsw_result* out, uint32_t* cells)
+Worker* get_worker(bsw_ctx* ctx, size_t k)
 {
-    if (!ctx || !out || (!tasks && n)) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    while (ctx->workers.size() <= k) {
+        std::unique_ptr<Worker> w(new Worker());
+        w->dev = (int)(ctx->workers.size() % ctx->devs.size());      // workers are dealt round-robin over the devices
+        ctx->workers.push_back(std::move(w));
+    }
+    return ctx->workers[k].get();
+}
+
+// The engine behind every batch entry point.  The batch is cut into chunks; `nworkers` host threads each run a
+// pipeline (fill -> validate -> plan -> pack -> H2D -> kernels -> D2H -> scatter) over the chunks they pull from a
+// shared counter, alternating between their two stream slots.  Workers are bound round-robin to the devices, so a
+// multi-GPU context balances dynamically -- the GPU analogue of task_parse handing the next task to the first PE
+// with room (sw_pe_array_task_parse.v:1600-1650).  No collective: results land in out[task].
+int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+{
+    if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (n == 0) return BSW_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
     const double w0 = now_ms();
@@ -292,67 +360,124 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const ExtTask* tasks,
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
-    std::vector<uint8_t> cls(n);
-    size_t bad = 0; std::string msg;
-    rc = validate_tasks(tasks, n, max_mat, opt, cls.data(), &bad, &msg);
-    if (rc) { set_error(ctx, msg); return rc; }
-
-    // shard over devices by estimated cells (contiguous ranges), then chunk
+    const size_t chunk = std::max<size_t>(32, ctx->chunk_tasks);
+    const size_t nchunks = (n + chunk - 1) / chunk;
     const size_t ndev = ctx->devs.size();
-    std::vector<size_t> cut(ndev + 1, n);
-    cut[0] = 0;
-    if (ndev > 1) {
-        std::vector<uint64_t> pre(n + 1, 0);
-        for (size_t i = 0; i < n; ++i) {
-            const int64_t band = std::min<int64_t>(tasks[i].qlen, 2 * (int64_t)tasks[i].w + 1);
-            pre[i + 1] = pre[i] + (uint64_t)(band * tasks[i].tlen) + 64;
-        }
-        for (size_t d = 1; d < ndev; ++d) {
-            const uint64_t target = pre[n] / ndev * d;
-            cut[d] = (size_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
-            if (cut[d] < cut[d - 1]) cut[d] = cut[d - 1];
-            if (cut[d] > n) cut[d] = n;
-        }
-    }
-    std::vector<int> dev_rc(ndev, 0);
-    SchedOptions dopt = opt;
-    dopt.host_threads = std::max(1, opt.host_threads / (int)ndev);
-    auto dev_worker = [&](size_t d) {
-        Device& D = ctx->devs[d];
-        if (cudaSetDevice(D.id) != cudaSuccess) { dev_rc[d] = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); return; }
-        size_t pos = cut[d];
-        const size_t end = cut[d + 1];
-        size_t k = 0;
+    size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
+    if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
+    if (nworkers < 1) nworkers = 1;
+    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
+
+    std::atomic<size_t> next(0);
+    std::atomic<int> first_err(0);
+    std::mutex stat_mu;
+    LocalStats total;
+
+    auto worker_main = [&](size_t k) {
+        Worker& W = *ctx->workers[k];
+        LocalStats st;
         int r = 0;
-        while (pos < end && !r) {
-            Slot& s = D.slots[k % D.slots.size()];
-            r = slot_collect(ctx, s, out, cells, dopt, true);
-            if (r) break;
-            const size_t cnt = std::min(ctx->chunk_tasks, end - pos);
-            r = slot_submit(ctx, s, tasks, cls.data(), pos, cnt, dp, sym, dopt, true);
-            pos += cnt; ++k;
+        if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
+        if (!r && !W.ready) {
+            for (Slot& s : W.slots) if (!r) r = slot_init(ctx, s);
+            W.ready = (r == 0);
         }
-        for (Slot& s : D.slots) {
-            const int r2 = slot_collect(ctx, s, out, cells, dopt, true);
-            if (!r) r = r2;
+        int cur = 0;
+        const bool trace = getenv("BSW_TRACE") != nullptr;
+        std::string tr;
+        auto T = [&]() { return now_ms() - w0; };
+        if (trace) tr += "w" + std::to_string(k) + " start " + std::to_string(T()) + "\n";
+        while (!r && !first_err.load(std::memory_order_relaxed)) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            Slot& s = W.slots[cur];
+            cur ^= 1;
+            const double c0 = T();
+            if ((r = slot_collect(ctx, s, out, cells, &st))) break;
+            if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(c) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
+            const size_t first = c * chunk, count = std::min(chunk, n - first);
+            const double v0 = now_ms();
+            s.tasks.resize(count);
+            src.fill(src.self, first, count, s.tasks.data());
+            st.validate_ms += now_ms() - v0;
+            const double f1 = T();
+            r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st);
+            if (trace) tr += " fill.." + std::to_string(f1) + " submitted " + std::to_string(T()) + "\n";
         }
-        if (r) {                      // leave the device quiescent on error
-            for (Slot& s : D.slots) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }
+        if (trace) tr += "w" + std::to_string(k) + " drain " + std::to_string(T());
+        for (Slot& s : W.slots) {
+            if (r) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }    // leave the device quiescent
+            else r = slot_collect(ctx, s, out, cells, &st);
         }
-        dev_rc[d] = r;
+        if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
+        if (trace) { tr += " done " + std::to_string(T()) + "\n"; fputs(tr.c_str(), stderr); }
+        std::lock_guard<std::mutex> g(stat_mu);
+        total.pack_ms += st.pack_ms; total.validate_ms += st.validate_ms; total.kernel_ms += st.kernel_ms;
+        total.h2d += st.h2d; total.d2h += st.d2h; total.launches += st.launches; total.tasks += st.tasks; total.cells += st.cells;
     };
-    if (ndev == 1) dev_worker(0);
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    if (nworkers == 1) worker_main(0);
     else {
         std::vector<std::thread> th;
-        for (size_t d = 0; d < ndev; ++d) th.emplace_back(dev_worker, d);
+        for (size_t k = 1; k < nworkers; ++k) th.emplace_back(worker_main, k);
+        worker_main(0);
         for (auto& t : th) t.join();
     }
-    for (size_t d = 0; d < ndev; ++d) if (dev_rc[d]) return dev_rc[d];
+    cudaSetDevice(prev_dev);
     {
         std::lock_guard<std::mutex> g(ctx->err_mu);
-        ctx->stats.wall_ms += now_ms() - w0;
+        bsw_stats& S = ctx->stats;
+        S.tasks += total.tasks; S.cells_band += total.cells; S.kernel_launches += total.launches;
+        S.h2d_bytes += total.h2d; S.d2h_bytes += total.d2h; S.kernel_ms += total.kernel_ms;
+        S.pack_ms += (total.pack_ms + total.validate_ms) / (double)nworkers;     // average per worker = wall share
+        S.wall_ms += now_ms() - w0;
     }
-    return BSW_OK;
+    return first_err.load();
+}
+
+// ---- task sources ----
+struct FlatSrc {
+    const bsw_params* p; const uint8_t* qbuf; const int64_t* qoff; const uint8_t* tbuf; const int64_t* toff;
+    const int32_t* h0; const int32_t* w;
+};
+void fill_flat(const void* self, size_t first, size_t count, ExtTask* out)
+{
+    const FlatSrc& S = *static_cast<const FlatSrc*>(self);
+    const bsw_params* p = S.p;
+    int last_q = -1, last_w = -1, last_c = -1;
+    for (size_t k = 0; k < count; ++k) {
+        const size_t i = first + k;
+        ExtTask& x = out[k];
+        const int64_t ql = S.qoff[i + 1] - S.qoff[i], tl = S.toff[i + 1] - S.toff[i];
+        x.q = S.qbuf + S.qoff[i]; x.t = S.tbuf + S.toff[i];
+        x.qlen = (ql < 0 || ql > 0x7fffffff) ? -1 : (int32_t)ql;
+        x.tlen = (tl < 0 || tl > 0x7fffffff) ? -1 : (int32_t)tl;
+        x.h0 = S.h0[i];
+        if (x.qlen >= 1 && S.w[i] >= 0) {
+            if (x.qlen != last_q || S.w[i] != last_w) {
+                last_q = x.qlen; last_w = S.w[i];
+                last_c = clamp_band(p->mat, x.qlen, S.w[i], p->end_bonus, p->o_ins, p->e_ins, p->o_del, p->e_del);
+            }
+            x.w = last_c;
+        } else x.w = -1;
+    }
+}
+struct RecSrc { const bsw_params* p; const bsw_task* tasks; };
+void fill_records(const void* self, size_t first, size_t count, ExtTask* out)
+{
+    const RecSrc& S = *static_cast<const RecSrc*>(self);
+    const bsw_params* p = S.p;
+    for (size_t k = 0; k < count; ++k) {
+        const bsw_task& t = S.tasks[first + k];
+        ExtTask& x = out[k];
+        x.q = t.query; x.t = t.target; x.qlen = t.qlen; x.tlen = t.tlen; x.h0 = t.h0;
+        x.w = (t.qlen >= 1 && t.w >= 0) ? clamp_band(p->mat, t.qlen, t.w, p->end_bonus, p->o_ins, p->e_ins, p->o_del, p->e_del) : -1;
+    }
+}
+void fill_vector(const void* self, size_t first, size_t count, ExtTask* out)
+{
+    memcpy(out, static_cast<const ExtTask*>(self) + first, count * sizeof(ExtTask));
 }
 
 }  // namespace
@@ -391,13 +516,12 @@ int bsw_init(bsw_ctx** out, const int* device_ids, int n_devices, int streams_pe
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, id) != cudaSuccess) return BSW_ECUDA;
         if (prop.major < 10) return BSW_ECUDA;                       // kernels are built for sm_100a only
-        Device D; D.id = id;
-        D.slots.resize((size_t)streams_per_device);
-        ctx->devs.push_back(std::move(D));
-        for (Slot& s : ctx->devs.back().slots)
-            if (slot_init(ctx.get(), s)) { bsw_destroy(ctx.release()); cudaSetDevice(prev); return BSW_ECUDA; }
+        ctx->devs.emplace_back();
+        ctx->devs.back().id = id;
+        if (slot_init(ctx.get(), ctx->devs.back().aux)) { bsw_destroy(ctx.release()); cudaSetDevice(prev); return BSW_ECUDA; }
     }
     cudaSetDevice(prev);
+    ctx->streams_per_device = streams_per_device;
     ctx->async.resize(16);
     *out = ctx.release();
     return BSW_OK;
@@ -409,9 +533,14 @@ void bsw_destroy(bsw_ctx* ctx)
     for (auto& a : ctx->async) if (a.used && a.fut.valid()) a.fut.wait();
     int prev = 0;
     cudaGetDevice(&prev);
+    for (auto& W : ctx->workers) {
+        cudaSetDevice(ctx->devs[(size_t)W->dev].id);
+        for (Slot& s : W->slots) { if (s.stream) cudaStreamSynchronize(s.stream); slot_free(s); }
+    }
     for (Device& D : ctx->devs) {
         cudaSetDevice(D.id);
-        for (Slot& s : D.slots) { if (s.stream) cudaStreamSynchronize(s.stream); slot_free(s); }
+        if (D.aux.stream) cudaStreamSynchronize(D.aux.stream);
+        slot_free(D.aux);
     }
     cudaSetDevice(prev);
     delete ctx;
@@ -430,6 +559,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
     else { set_error(ctx, "unknown option " + k); return BSW_EINVAL; }
     return BSW_OK;
@@ -441,18 +571,8 @@ int bsw_extend_batch(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tas
     if (n == 0) return BSW_OK;
     if (!params || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
-    std::vector<ExtTask> v(n);
-    const int nt = ctx->opt.host_threads;
-    pfor(n, 16384, nt, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) {
-            const bsw_task& t = tasks[i];
-            ExtTask& x = v[i];
-            x.q = t.query; x.t = t.target; x.qlen = t.qlen; x.tlen = t.tlen; x.h0 = t.h0;
-            x.w = (t.qlen >= 1 && t.w >= 0) ? clamp_band(params->mat, t.qlen, t.w, params->end_bonus, params->o_ins,
-                                                         params->e_ins, params->o_del, params->e_del) : -1;
-        }
-    });
-    return run_extensions(ctx, params, v.data(), n, out, nullptr);
+    const RecSrc S{ params, tasks };
+    return run_extensions(ctx, params, TaskSource{ &S, fill_records }, n, out, nullptr);
 }
 
 int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t* qbuf, const int64_t* qoff,
@@ -463,23 +583,8 @@ int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t*
     if (n == 0) return BSW_OK;
     if (!params || !qbuf || !qoff || !tbuf || !toff || !h0 || !w || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
-    std::vector<ExtTask> v(n);
-    std::atomic<int> bad(0);
-    pfor(n, 16384, ctx->opt.host_threads, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) {
-            ExtTask& x = v[i];
-            const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
-            if (ql < 0 || tl < 0 || ql > 0x7fffffff || tl > 0x7fffffff) bad.store(1);
-            x.q = qbuf + qoff[i]; x.t = tbuf + toff[i];
-            x.qlen = (int32_t)std::max<int64_t>(std::min<int64_t>(ql, 0x7fffffff), -1);
-            x.tlen = (int32_t)std::max<int64_t>(std::min<int64_t>(tl, 0x7fffffff), -1);
-            x.h0 = h0[i];
-            x.w = (x.qlen >= 1 && w[i] >= 0) ? clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins,
-                                                          params->e_ins, params->o_del, params->e_del) : -1;
-        }
-    });
-    if (bad.load()) { set_error(ctx, "offsets are not monotone"); return BSW_EINVAL; }
-    return run_extensions(ctx, params, v.data(), n, out, cells);
+    const FlatSrc S{ params, qbuf, qoff, tbuf, toff, h0, w };
+    return run_extensions(ctx, params, TaskSource{ &S, fill_flat }, n, out, cells);
 }
 
 // ---------------- level 2: fused seed task (left + right extension, band retry, clip) ----------------
@@ -529,7 +634,7 @@ int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* 
                 ext.push_back(x); who.push_back(i);
             }
             res.resize(ext.size());
-            const int rc = run_extensions(ctx, &pp, ext.data(), ext.size(), res.data(), nullptr);
+            const int rc = run_extensions(ctx, &pp, TaskSource{ ext.data(), fill_vector }, ext.size(), res.data(), nullptr);
             if (rc) return rc;
             std::vector<size_t> again;
             for (size_t e = 0; e < who.size(); ++e) {
@@ -633,18 +738,17 @@ int bsw_resident_create(bsw_ctx* ctx, const bsw_params* params, const uint8_t* q
         x.w = (x.qlen >= 1 && w[i] >= 0) ? clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins,
                                                       params->e_ins, params->o_del, params->e_del) : -1;
     }
-    std::vector<uint8_t> cls(n);
-    size_t bad = 0; std::string msg;
-    rc = validate_tasks(v.data(), n, max_mat, opt, cls.data(), &bad, &msg);
-    if (rc) { set_error(ctx, msg); return rc; }
-    R->dev = ctx->devs[0].id; R->n = n;
+    R->dev = ctx->devs[0].id; R->n = n; R->variant = opt.variant;
     int prev = 0;
     cudaGetDevice(&prev);
     CUDA_TRY(ctx, cudaSetDevice(R->dev));
     rc = slot_init(ctx, R->slot);
     if (!rc) {
         // submit once: this packs, uploads and runs the batch; later runs reuse the device-resident plan
-        rc = slot_submit(ctx, R->slot, v.data(), cls.data(), 0, n, R->dp, R->sym, opt, true);
+        LocalStats st;
+        R->slot.tasks.swap(v);
+        rc = slot_submit(ctx, R->slot, 0, n, max_mat, R->dp, R->sym, opt, false, &st);
+        std::vector<ExtTask>().swap(R->slot.tasks);
         if (!rc) { cudaError_t e = cudaStreamSynchronize(R->slot.stream); if (e != cudaSuccess) rc = cuda_fail(ctx, e, "resident upload"); }
         R->slot.busy = false;
     }
@@ -666,15 +770,10 @@ int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t*
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     size_t nl = 0;
-    for (const Launch& L : P.launches) {
-        LaunchArgs a{};
-        a.tiles = s.d_tiles + L.tile0; a.slots = s.d_slots; a.arena = s.d_arena; a.out = s.d_out;
-        a.cells_total = s.d_cells; a.p = R->dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
-        cudaError_t e = (L.kind == 1) ? k1_launch(a, ctx->opt.variant, L.generic, R->sym, s.stream)
-                                      : k2_launch(a, L.generic, s.stream);
-        if (e != cudaSuccess) { cudaSetDevice(prev); return cuda_fail(ctx, e, "resident launch"); }
-        ++nl;
-    }
+    { int rc = enqueue_gather(ctx, s);                  // the device half of the scheduler is part of every pass
+      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl);
+      if (rc) { cudaSetDevice(prev); return rc; }
+      if (s.plan.n_k1_tiles) ++nl; }
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
@@ -752,7 +851,7 @@ int bsw_measure_int_peak(bsw_ctx* ctx, int device_index, bsw_int_peak* out)
     cudaGetDevice(&prev);
     CUDA_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)device_index].id));
     double ops[5] = { 0, 0, 0, 0, 0 }; double mhz = 0; int sms = 0;
-    cudaError_t e = int_peak_run(ops, &mhz, &sms, ctx->devs[(size_t)device_index].slots[0].stream);
+    cudaError_t e = int_peak_run(ops, &mhz, &sms, ctx->devs[(size_t)device_index].aux.stream);
     cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "int peak micro-benchmark");
     out->iadd_tops = ops[0] * 1e-12; out->vimnmx_tops = ops[1] * 1e-12; out->dpx_tops = ops[2] * 1e-12; out->mix_tops = ops[3] * 1e-12; out->dual_tops = ops[4] * 1e-12;

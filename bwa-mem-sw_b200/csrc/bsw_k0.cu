@@ -1,0 +1,54 @@
+// bsw_k0.cu -- K0: tile gather, the device half of the task scheduler (sm_100a).
+//
+// The host packs every sequence exactly once, in input order, into a task-major source arena (sequential reads and
+// writes at memory speed, bsw_sched.cpp::pack_tasks) and only sorts task *indices*.  This kernel plays the part of
+// sw_pe_array_task_parse's data path (sw_pe_array_task_parse.v:924-948: fetch each task's words from the batch buffer
+// and hand them to its PE): one warp per K1 tile copies the 32 tasks' packed words into the tile-interleaved layout
+// q[k*32+lane] / t[k*32+lane] that K1 consumes with one TMA bulk copy and coalesced 128-byte target loads.
+// Reads are 128-bit per lane (each lane walks its own task), writes are full 128-byte lines.
+#include <cuda_runtime.h>
+#include "bsw_device.cuh"
+#include "bsw_kernels.h"
+
+namespace bsw {
+
+constexpr int K0_WARPS = 4;
+
+__device__ __forceinline__ void k0_copy_block(const uint4* __restrict__ src16, int own_words, uint32_t* __restrict__ dst,
+                                              int tile_words, int lane)
+{
+    for (int m = 0; m * 4 < tile_words; ++m) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (m * 4 < own_words) v = __ldg(src16 + m);
+        uint32_t* d = dst + (size_t)(m * 4) * TILE_LANES + lane;
+        d[0] = v.x;
+        if (m * 4 + 1 < tile_words) d[TILE_LANES] = v.y;
+        if (m * 4 + 2 < tile_words) d[2 * TILE_LANES] = v.z;
+        if (m * 4 + 3 < tile_words) d[3 * TILE_LANES] = v.w;
+    }
+}
+
+__global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_constant__ GatherArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * K0_WARPS + (threadIdx.x >> 5);
+    if (tile >= A.ntiles) return;
+    const TileHdr hd = A.tiles[tile];
+    const int nqw = (int)(hd.nqw_ntw & 0xffffu), ntw = (int)(hd.nqw_ntw >> 16);
+    const SlotParam sp = A.slots[hd.slot0 + lane];
+    const SlotSrc ss = A.slot_src[hd.slot0 + lane];
+    const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0;      // words the host packed for this task (zero padded)
+    const int own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
+    const uint4* src16 = reinterpret_cast<const uint4*>(A.src);
+    k0_copy_block(src16 + ss.qoff16, own_q, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
+    k0_copy_block(src16 + ss.toff16, own_t, A.dst + (size_t)hd.toff16 * 4, ntw, lane);
+}
+
+cudaError_t k0_launch(const GatherArgs& a, cudaStream_t st)
+{
+    if (!a.ntiles) return cudaSuccess;
+    k0_gather_kernel<<<(a.ntiles + K0_WARPS - 1) / K0_WARPS, K0_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace bsw

@@ -86,7 +86,10 @@ static cudaError_t k1_launch_t(const LaunchArgs& a, cudaStream_t st)
     if (!a.ntiles) return cudaSuccess;
     const size_t smem = k1_smem_bytes(a.qmax, a.nqw_max);
     auto kern = k1_extend_kernel<VARIANT, GENERIC, SYM>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
+    // value would race with another thread's launch of the same kernel
+    if (smem > 232448) return cudaErrorInvalidValue;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles, K1_NT, smem, st>>>(a);
     return cudaGetLastError();

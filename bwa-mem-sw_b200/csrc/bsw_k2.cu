@@ -251,7 +251,10 @@ static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
     if (!a.ntiles) return cudaSuccess;
     const size_t smem = k2_smem_bytes(a.qmax);
     auto kern = k2_extend_kernel<GENERIC>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
+    // value would race with another thread's launch of the same kernel
+    if (smem > 232448) return cudaErrorInvalidValue;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles, K2_NT, smem, st>>>(a);
     return cudaGetLastError();

@@ -1,9 +1,14 @@
 // bsw_sched.h -- host-side length-bucketed task scheduler and sequence packer.
 //
-// Plays the role of sw_pe_array_task_parse (sw_pe_array_task_parse.v:1600-1650,1652-1762: parse the
-// batch, hand every task to a PE) and of the host code that fills the task batch buffer (layout in
-// SURVEY.md App. A.1).  Pure host code, no CUDA: it is unit-tested on the CPU (tests/test_sched.py via
-// the emulation harness) and used unchanged by the product library.
+// Plays the role of the host code that fills the task batch buffer (layout in SURVEY.md App. A.1) and of
+// sw_pe_array_task_parse (sw_pe_array_task_parse.v:1600-1650,1652-1762: parse the batch, hand every task to a PE).
+// Pure host code, no CUDA: it is unit-tested on the CPU through the emulation harness and used unchanged by
+// the product library.  Per chunk of tasks:
+//   1. pack_tasks   one streaming pass over the caller's bases: validate the codes, detect N, pack 4 bit/base into the
+//                   TASK-MAJOR source arena (each sequence 16-byte aligned) -- sequential reads, sequential writes;
+//   2. build_plan   radix-sort the chunk by (class, qlen, tlen, h0), cut it into 32-task tiles and into launches
+//                   bucketed by shared-memory occupancy; K1 tiles get a block in the TILED arena, which the device
+//                   fills from the source arena (k0 gather kernel, bsw_k0.cu); K2 tiles read the source arena directly.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -40,30 +45,35 @@ struct Launch {
 };
 
 struct Plan {
-    std::vector<TileHdr>   tiles;
+    std::vector<TileHdr>   tiles;        // K1 tiles first (their blocks live in the tiled arena), then K2 tiles
     std::vector<SlotParam> slots;
+    std::vector<SlotSrc>   slot_src;     // where each slot's packed query / target sit in the source arena
     std::vector<int64_t>   slot_task;    // task index (into the chunk) of every slot, -1 = padding lane
     std::vector<Launch>    launches;
-    size_t arena_words = 0;              // size of the packed sequence arena (multiple of 32 words)
+    uint32_t n_k1_tiles = 0;
+    size_t tiled_words = 0;              // size of the tiled arena (device only)
     uint64_t est_cells = 0;
+    // scratch reused across calls (radix sort of the chunk)
+    std::vector<uint32_t> key, order, tmp, hist;
 };
 
-// Per-task classification produced by validate(): bit0 = contains N (needs GENERIC), bit1 = long (K2).
-// Returns 0 or a negative BSW_E* code; on error *bad_task is the offending task and msg explains.
-int validate_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt,
-                   uint8_t* cls, size_t* bad_task, std::string* msg);
+// Upper bound of the source arena for these tasks, in u32 words (16-byte aligned sequences + slack).
+size_t source_arena_bound(const ExtTask* tasks, size_t n);
 
-// Sort, tile, bucket.  cls from validate_tasks.
-void build_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan);
+// Fused validate + classify + pack (single pass, single thread).  cls: bit0 = needs matrix-lookup scoring (contains N,
+// or the matrix is not +a/-b), bit1 = long task (K2).  src[i] = offsets of task i's packed sequences in `arena`.
+// Returns 0 or a negative BSW_E* code; on error *bad_task is the first offending task and msg explains.
+int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
+               uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
 
-// Write the packed sequences of the plan into arena (plan->arena_words u32, 128-byte aligned).
-void pack_arena(const ExtTask* tasks, const Plan& plan, const SchedOptions& opt, uint32_t* arena);
+// Sort, tile, bucket.  Single-threaded: the driver runs one plan per chunk per host thread.
+void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t n, const SchedOptions& opt, Plan* plan);
 
 // ksw_extend2's band clamp (public BWA algorithm; the RTL takes max_ins/max_del precomputed from the host:
 // sw_pe_array_proc_element.v:924-934 and applies them at sw_pe_array_sw_extend.v:1763-1765,1881,1890).
 int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, int e_ins, int o_del, int e_del);
 
-// Simple fork-join helper used by the scheduler, the packer and the result scatter.
+// Simple fork-join helper.
 void parallel_for(size_t n, size_t grain, int nthreads, const void* ctx,
                   void (*fn)(const void* ctx, size_t lo, size_t hi));
 int default_host_threads();

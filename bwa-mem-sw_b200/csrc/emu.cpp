@@ -5,6 +5,8 @@
 // CPU, lane by lane, over emulated shared-memory arrays.  This lets `pytest -m "not gpu"` check the scheduler, the
 // packer and the K1 control flow (lazy narrowing, partial chunks, DPX identities) against the oracle without a GPU.
 // The CUDA kernels themselves are only ever checked on a GPU (`pytest -m gpu`).
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,6 +35,23 @@ void run_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, co
         const uint32_t* tg = arena + (size_t)hd.toff16 * 4 + lane;
         k1_task<VARIANT, GENERIC, SYM>(dp, sp.qlen, sp.tlen, sp.h0, sp.w, eh.data() + lane, qs.data() + lane, tg,
                                        out[hd.slot0 + lane]);
+    }
+}
+
+// Host restatement of the k0 gather kernel (bsw_k0.cu): lane l of a K1 tile copies its task's packed words from the
+// task-major source arena into the tile-interleaved block.
+void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
+{
+    for (uint32_t t = 0; t < P.n_k1_tiles; ++t) {
+        const TileHdr& hd = P.tiles[t];
+        const int nqw = (int)(hd.nqw_ntw & 0xffffu), ntw = (int)(hd.nqw_ntw >> 16);
+        for (int lane = 0; lane < TILE_LANES; ++lane) {
+            const SlotParam& sp = P.slots[hd.slot0 + lane];
+            const SlotSrc& ss = P.slot_src[hd.slot0 + lane];
+            const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0, own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
+            for (int k = 0; k < nqw; ++k) dst[(size_t)hd.qoff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_q ? src[(size_t)ss.qoff16 * 4 + k] : 0u;
+            for (int k = 0; k < ntw; ++k) dst[(size_t)hd.toff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_t ? src[(size_t)ss.toff16 * 4 + k] : 0u;
+        }
     }
 }
 
@@ -75,13 +94,16 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
                                                       params->e_ins, params->o_del, params->e_del) : -1;
     }
     std::vector<uint8_t> cls(n);
-    size_t bad = 0; std::string msg;
-    int rc = validate_tasks(v.data(), n, mx, opt, cls.data(), &bad, &msg);
+    std::vector<SlotSrc> ssrc(n);
+    std::vector<uint32_t> src(source_arena_bound(v.data(), n), 0xdeadbeefu);
+    size_t bad = 0, used = 0; std::string msg;
+    int rc = pack_tasks(v.data(), n, mx, opt, cls.data(), ssrc.data(), src.data(), &used, &bad, &msg);
     if (rc) return rc;
+    if (used > src.size()) return BSW_ENOMEM;
     Plan P;
-    build_plan(v.data(), cls.data(), n, opt, &P);
-    std::vector<uint32_t> arena(P.arena_words + 64, 0xdeadbeefu);
-    pack_arena(v.data(), P, opt, arena.data());
+    build_plan(v.data(), cls.data(), ssrc.data(), n, opt, &P);
+    std::vector<uint32_t> arena(P.tiled_words + 64, 0xdeadbeefu);
+    gather_host(P, src.data(), arena.data());
     std::vector<SlotResult> res(P.slots.size());
     for (const Launch& L : P.launches) {
         if (L.kind != 1) return BSW_ERANGE;
@@ -102,8 +124,58 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
         if (cells) cells[t] = (uint32_t)r.cells;
     }
-    if (info) { info[0] = (int64_t)P.launches.size(); info[1] = (int64_t)P.tiles.size(); info[2] = (int64_t)P.arena_words; info[3] = (int64_t)pad; }
+    if (info) { info[0] = (int64_t)P.launches.size(); info[1] = (int64_t)P.tiles.size(); info[2] = (int64_t)P.tiled_words; info[3] = (int64_t)pad; }
     return BSW_OK;
 }
 
 }  // extern "C"
+
+// Host-path profiler (tests/dev only): the per-chunk host pipeline of bsw_host.cpp's workers without the CUDA calls.
+// ms[0..2] = fill, validate+pack, plan (cpu-ms summed over chunks), ms[4] = wall; `threads` chunks in flight.
+extern "C" int bsw_emu_host_phases(const bsw_params* params, const uint8_t* qbuf, const int64_t* qoff, const uint8_t* tbuf,
+                                   const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n, int threads, size_t chunk,
+                                   double* ms)
+{
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    SchedOptions opt;
+    opt.host_threads = 1; opt.fast_matrix = true;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    struct Scratch { std::vector<ExtTask> v; std::vector<uint8_t> cls; std::vector<SlotSrc> ss; Plan P; std::vector<uint32_t> arena; double t[4] = {0, 0, 0, 0}; };
+    static std::vector<Scratch> sc;
+    if (sc.size() < (size_t)threads) sc.resize((size_t)threads);
+    std::atomic<size_t> next(0);
+    std::atomic<int> slot(0);
+    const double w0 = now();
+    pfor((size_t)threads, 1, threads, [&](size_t, size_t) {
+        Scratch& S = sc[(size_t)slot.fetch_add(1)];
+        for (int k = 0; k < 4; ++k) S.t[k] = 0;
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            const size_t first = c * chunk, cnt = std::min(chunk, n - first);
+            double t0 = now();
+            S.v.resize(cnt); S.cls.resize(cnt); S.ss.resize(cnt);
+            int last_q = -1, last_c = 0;
+            for (size_t k = 0; k < cnt; ++k) {
+                const size_t i = first + k;
+                ExtTask& x = S.v[k];
+                x.q = qbuf + qoff[i]; x.t = tbuf + toff[i];
+                x.qlen = (int32_t)(qoff[i + 1] - qoff[i]); x.tlen = (int32_t)(toff[i + 1] - toff[i]); x.h0 = h0[i];
+                if (x.qlen != last_q) { last_q = x.qlen; last_c = clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del); }
+                x.w = last_c;
+            }
+            double t1 = now();
+            const size_t bound = source_arena_bound(S.v.data(), cnt);
+            if (S.arena.size() < bound) S.arena.resize(bound + bound / 4);
+            size_t bad = 0, used = 0; std::string msg;
+            pack_tasks(S.v.data(), cnt, 1, opt, S.cls.data(), S.ss.data(), S.arena.data(), &used, &bad, &msg);
+            double t2 = now();
+            build_plan(S.v.data(), S.cls.data(), S.ss.data(), cnt, opt, &S.P);
+            double t3 = now();
+            S.t[0] += t1 - t0; S.t[1] += t2 - t1; S.t[2] += t3 - t2;
+        }
+    });
+    ms[4] = now() - w0;
+    for (int k = 0; k < 4; ++k) { ms[k] = 0; for (int t = 0; t < threads; ++t) ms[k] += sc[(size_t)t].t[k]; }
+    return 0;
+}

@@ -54,7 +54,8 @@ void bsw_destroy(bsw_ctx *ctx);
 const char *bsw_last_error(const bsw_ctx *ctx);          /* thread-unsafe convenience: last error text of this ctx */
 const char *bsw_version(void);
 /* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity);
- * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode) */
+ * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
+ * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 1) */
 int  bsw_set_option(bsw_ctx *ctx, const char *key, int64_t value);
 int  bsw_num_devices(const bsw_ctx *ctx);
 

@@ -48,7 +48,7 @@ def timing(ctx, name, n, reps=3, opts=None):
     ctx.set_option("force_kernel", 0)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "sweep"):
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = B.Context()
     fails = 0
@@ -70,3 +70,32 @@ if __name__ == "__main__":
         timing(ctx, "cfg4_long", 2000)
     print("FAILS", fails)
     sys.exit(1 if fails else 0)
+
+
+def e2e_sweep():
+    import torch
+    ctx = B.Context()
+    t = B.synth_tasks("cfg2_150bp", 1000000)
+    p = B.make_params()
+    flat = (t['qbuf'], t['qoff'], t['tbuf'], t['toff'], t['h0'], t['w'])
+    x = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); y = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); y.copy_(x, non_blocking=True); torch.cuda.synchronize(); t1 = time.perf_counter()
+        x.copy_(y, non_blocking=True); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"[pcie] H2D {0.268/(t1-t0):.1f} GB/s  D2H {0.268/(t2-t1):.1f} GB/s", flush=True)
+    for threads in (16, 8):
+        for chunk in (8192, 16384, 32768, 65536, 131072):
+            ctx.set_option("chunk_tasks", chunk); ctx.set_option("host_threads", threads)
+            for _ in range(3):
+                ctx.sw_extend_batch(p, *flat, want_cells=False)
+            ctx.reset_stats()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ctx.sw_extend_batch(p, *flat, want_cells=False)
+            dt = (time.perf_counter() - t0) / 5
+            st = ctx.stats()
+            print(f"[e2e] threads={threads} chunk={chunk}: {dt*1e3:.2f} ms/step  pack_ms/worker={st['pack_ms']/5:.2f} kernel_ms(sum)={st['kernel_ms']/5:.2f} launches={st['kernel_launches']//5}", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    e2e_sweep()
