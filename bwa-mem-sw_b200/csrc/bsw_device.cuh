@@ -48,6 +48,7 @@ struct DevParams {
     int32_t match, mismatch;       // FAST scoring: +match / -mismatch (mismatch stored positive)
     uint32_t row_lo[5], row_hi[5]; // GENERIC scoring: row t of the 5x5 matrix as bytes {s(t,0..3)} / {s(t,4),0,0,0}
     int8_t  mat[28];               // the 5x5 matrix itself (K2 GENERIC lookup), padded
+    uint32_t zero;                 // always 0: a zero the compiler cannot fold (keeps it in one register, see bsw_k1_core.cuh)
 };
 
 // k0: gather launch = K1 tiles [0, ntiles) of `tiles`; copies src words of every lane into the tiled arena.

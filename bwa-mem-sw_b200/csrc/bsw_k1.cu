@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
     const uint32_t nqw = hd.nqw_ntw & 0xffffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* qs = reinterpret_cast<uint32_t*>(smem_raw + K1_HDR_BYTES);
-    uint32_t* eh = qs + (size_t)(A.nqw_max + 1) * K1_NT;
+    uint32_t* eh = qs + (size_t)(A.nqw_max + K1_QS_EXTRA) * K1_NT;
     const uint32_t qbytes = nqw * K1_NT * 4u;
 
     if (lane == 0) {
@@ -46,7 +46,6 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
     }
     const uint32_t slot = hd.slot0 + lane;
     const SlotParam sp = A.slots[slot];
-    qs[nqw * K1_NT + lane] = 0;                      // one zero word past the block for the funnel shift
     __syncwarp();
     {
         const uint32_t bar = smem_u32(mbar);
@@ -63,7 +62,7 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
     if (sp.qlen > 0) {
         const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u + lane;
         SlotResult r;
-        k1_task<VARIANT, GENERIC, SYM>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, eh + lane, qs + lane, tg, r);
+        k1_task<VARIANT, GENERIC, SYM>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, (int)nqw, eh + lane, qs + lane, tg, r);
         int4* o = reinterpret_cast<int4*>(A.out + slot);
         o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
         o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
 
 size_t k1_smem_bytes(int qmax, int nqw_max)
 {
-    return (size_t)K1_HDR_BYTES + ((size_t)(nqw_max + 1) + (size_t)(qmax + 1 + K1_EH_SLACK)) * K1_NT * 4u;
+    return (size_t)K1_HDR_BYTES + ((size_t)(nqw_max + K1_QS_EXTRA) + (size_t)(qmax + 1 + K1_EH_SLACK)) * K1_NT * 4u;
 }
 
 template <int VARIANT, int GENERIC, int SYM>

@@ -29,6 +29,15 @@ constexpr int K2_HDR_BYTES = 128;
 
 __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Score of (target row, query nibble): FAST = +match / -mismatch by nibble XOR; GENERIC = byte lookup in the target base's
+// matrix row (the RTL's 25:1 mux, sw_pe_array_mux_25to1_sel5_8_1.v:105-142).
+template <int GENERIC>
+__device__ __forceinline__ int k2_score(uint32_t nib_or_xor, int mat, int mis, uint32_t rlo, uint32_t rhi)
+{
+    if (GENERIC) return k1_lookup(nib_or_xor, rlo, rhi);
+    return nib_or_xor ? mis : mat;
+}
+
 // bits [a, b] (inclusive, cell indices) of the 32-cell word that starts at cell `base`
 __device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
 {
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
-                const int s = k1_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
+                const int s = k2_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
                 hh[k] = add_max(M, s, e);                                          // sx:1797,1798
                 int g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
                 if (!full && !(k >= lo && k < hi)) g = 0;

@@ -150,7 +150,7 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
 
 static inline size_t k1_tile_smem(int qmax, int nqw)
 {
-    return 128 + ((size_t)(nqw + 1) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;
+    return 128 + ((size_t)(nqw + 8) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;
 }
 static inline size_t k2_task_smem(int qmax)
 {

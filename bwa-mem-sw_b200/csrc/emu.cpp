@@ -25,15 +25,14 @@ void run_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, co
               int qmax, int nqw_max)
 {
     const int nqw = (int)(hd.nqw_ntw & 0xffffu);
-    std::vector<uint32_t> qs((size_t)(nqw_max + 1) * K1_S, 0xdeadbeefu);
+    std::vector<uint32_t> qs((size_t)(nqw_max + K1_QS_EXTRA) * K1_S, 0xdeadbeefu);
     std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1_S, 0xdeadbeefu);
     memcpy(qs.data(), arena + (size_t)hd.qoff16 * 4, (size_t)nqw * K1_S * 4);       // the TMA bulk copy
-    for (int lane = 0; lane < K1_S; ++lane) qs[(size_t)nqw * K1_S + lane] = 0;
     for (int lane = 0; lane < K1_S; ++lane) {
         const SlotParam& sp = slots[hd.slot0 + lane];
         if (sp.qlen <= 0) continue;
         const uint32_t* tg = arena + (size_t)hd.toff16 * 4 + lane;
-        k1_task<VARIANT, GENERIC, SYM>(dp, sp.qlen, sp.tlen, sp.h0, sp.w, eh.data() + lane, qs.data() + lane, tg,
+        k1_task<VARIANT, GENERIC, SYM>(dp, sp.qlen, sp.tlen, sp.h0, sp.w, nqw, eh.data() + lane, qs.data() + lane, tg,
                                        out[hd.slot0 + lane]);
     }
 }
