@@ -10,6 +10,8 @@
 //   mode 4: IADD3 and IMAD interleaved (adds issued to both the ALU and the FMA pipe)
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include "bsw_kernels.h"
 
 namespace bsw {
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(PEAK_THREADS) int_peak_kernel(int iters, int a
             else if (MODE == 1) r[k] = max(r[k], o);
             else if (MODE == 2) r[k] = __viaddmax_s32(r[k], a, o);
             else if (MODE == 4) { if (k & 1) r[k] = r[k] * b + o; else r[k] = r[k] + o + a; }
+            else if (MODE == 5) r[k] = (int)__umulhi((unsigned)r[k], (unsigned)(b + 0x10000)) + o;
+            else if (MODE == 6) r[k] = (int)__byte_perm((unsigned)r[k], (unsigned)o, 0x7632);
         }
         if (MODE == 3) {
             // 4 independent cells per iteration: M,e,f,h1 state per chain; 13 ops each
@@ -103,6 +107,10 @@ cudaError_t int_peak_run(double out_ops[5], double* sm_clock_mhz, int* sm_count,
     if (e == cudaSuccess) e = run_mode<2>(grid, iters, d_out, d_clk, st, &ms[2]);
     if (e == cudaSuccess) e = run_mode<3>(grid, iters, d_out, d_clk, st, &ms[3]);
     if (e == cudaSuccess) e = run_mode<4>(grid, iters, d_out, d_clk, st, &ms[4]);
+    float ms5 = 0, ms6 = 0;
+    if (e == cudaSuccess) e = run_mode<5>(grid, iters, d_out, d_clk, st, &ms5);
+    if (e == cudaSuccess) e = run_mode<6>(grid, iters, d_out, d_clk, st, &ms6);
+    if (getenv("BSW_TRACE")) fprintf(stderr, "[intpeak] IMAD.HI stream %.2f Tops/s, PRMT stream %.2f Tops/s\n", (double)grid * PEAK_THREADS * iters * PEAK_ACC / (ms5 * 1e-3) * 1e-12, (double)grid * PEAK_THREADS * iters * PEAK_ACC / (ms6 * 1e-3) * 1e-12);
     long long clk[2] = { 0, 1 };
     if (e == cudaSuccess) e = cudaMemcpy(clk, d_clk, sizeof(clk), cudaMemcpyDeviceToHost);
     cudaFree(d_out); cudaFree(d_clk);

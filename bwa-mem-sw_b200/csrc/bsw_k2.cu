@@ -1,4 +1,4 @@
-// bsw_k2.cu -- K2: intra-task extension kernel for long tasks, one warp per task (sm_100a).
+// bsw_k2.cu -- K2: intra-task extension kernel for long tasks, one 4-warp CTA per task (sm_100a).
 //
 // The reference caps a task at qlen <= 255 / 2048 bases (query_mem 2048x4b, eh_arr 256 entries:
 // sw_pe_array_proc_element.v:347-350, sw_pe_array_sw_extend.v:512-515); BASELINE config 4 asks for
@@ -7,15 +7,19 @@
 // Why not an anti-diagonal wavefront: row i+1's window [beg,end) depends on the COMPLETE row i (arg-max
 // column mj and the non-zero run around it, sw_pe_array_sw_extend.v:1766-1769,1779,1782-1789), and the
 // narrowing is not result-neutral, so a wavefront that starts row i+1 before row i ends cannot be
-// bit-exact.  K2 is row-parallel instead: a warp sweeps one row at a time in groups of 256 columns, lane l
-// owning 8 consecutive columns (two 128-bit shared-memory accesses each way).  H and E only depend on the
-// previous row.  F is a max-plus linear recurrence along the row,
+// bit-exact.  K2 is row-parallel instead: the CTA sweeps one row at a time, warp g taking the g-th 256-column
+// group of the window (w = 500 gives a 1001-column band = 4 groups), lane l owning 8 consecutive columns (two
+// 128-bit shared-memory accesses each way).  H and E only depend on the previous row.  F is a max-plus linear
+// recurrence along the row,
 //     f[j+1] = max(f[j] - e_ins, g[j]),   g[j] = max(0, max(M[j]+s[j], e[j]) - oe_ins)
-// (g does not need f because f - oe_ins <= f - e_ins for o_ins >= 0), so each lane runs its 8 columns with
-// a zero carry-in, the carries are combined across lanes with a 5-step __shfl_up_sync prefix-max on
-// A[l] + 8*e_ins*l, and a second pass folds the carry into f/h and produces E, the row buffer, the packed
-// arg-max key and one "H == 0" bit per column.  The band narrowing is then two masked bit scans over
-// those bits (__clz/__ffs + REDUX), i.e. exactly the reference's two scan loops.
+// (g does not need f because f - oe_ins <= f - e_ins for o_ins >= 0), so
+//   pass 1: every lane runs its 8 columns with a zero carry-in; the carries are combined across lanes with a
+//           5-step __shfl_up_sync prefix-max on A[l] + 8*e_ins*l and across warps through shared memory
+//           (A_group - 256*e_ins*distance);
+//   pass 2: the carry is folded into f/h and E, the row buffer, the packed arg-max key (REDUX max) and one
+//           "H == 0" bit per column are produced.
+// The band narrowing is then two masked bit scans over those bits (__clz/__ffs + REDUX), i.e. exactly the
+// reference's two scan loops.  Three __syncthreads per row round.
 #include <cuda_runtime.h>
 #include "bsw_device.cuh"
 #include "bsw_k1_core.cuh"
@@ -23,9 +27,10 @@
 
 namespace bsw {
 
-constexpr int K2_NT = 32;
+constexpr int K2_WARPS = 4;
+constexpr int K2_NT = 32 * K2_WARPS;
 constexpr int K2_GROUP = 256;           // columns per warp step
-constexpr int K2_HDR_BYTES = 128;
+constexpr int K2_HDR_BYTES = 128;       // mbarrier (8 B) + cross-warp exchange words
 
 __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -50,7 +55,7 @@ template <int GENERIC>
 __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileHdr hd = A.tiles[blockIdx.x];
     const uint32_t slot = hd.slot0;
     const SlotParam sp = A.slots[slot];
@@ -60,12 +65,15 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
     const uint32_t qbytes = (uint32_t)((nqw * 4 + 15) & ~15);
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    int* xagg = reinterpret_cast<int*>(smem_raw + 16);                            // [K2_WARPS] group aggregate of pass 1
+    int* xhl  = xagg + K2_WARPS;                                                  // [K2_WARPS] h of the group's last column
+    int* xkey = xhl + K2_WARPS;                                                   // [K2_WARPS] per-warp arg-max key
     uint32_t* qs = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);          // qcap/8 words (+ pad)
     uint32_t* zb = qs + (qcap >> 3) + 4;                                          // qcap/32 words of zero bits
     uint32_t* eh = zb + (qcap >> 5) + 4;                                          // qcap + 8 words
     eh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(eh) + 15) & ~(uintptr_t)15);
 
-    if (lane == 0) {
+    if (tid == 0) {
         const uint32_t bar = k2_smem_u32(mbar), dst = k2_smem_u32(qs);
         const void* src = reinterpret_cast<const uint4*>(A.arena) + hd.qoff16;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -80,15 +88,15 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
     const int zdrop = A.p.zdrop;
     const int mat = A.p.match, mis = -A.p.mismatch;
     const uint32_t ce_pack = 0x8000u | ((uint32_t)(-e_del) << 16);
-    const int e8 = 8 * e_ins;
+    const int e8 = 8 * e_ins, e256 = K2_GROUP * e_ins;
 
     // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
-    for (int j = lane; j < qcap + 8; j += K2_NT) {
+    for (int j = tid; j < qcap + 8; j += K2_NT) {
         int hv = (j == 0) ? h0 : imax(h0 - A.p.o_ins - j * e_ins, 0);
         if (j > qlen) hv = 0;
         eh[j] = (uint32_t)hv;
     }
-    __syncwarp();
+    __syncthreads();                                   // mbarrier init + first row visible to every warp
     {
         const uint32_t bar = k2_smem_u32(mbar);
         uint32_t done = 0;
@@ -122,88 +130,113 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
             break;                                                                 // sx:1942
         }
 
-        int carry = 0;            // f entering lane 0's first column of the group
-        int hcarry = fc;          // h of the column left of the group
+        int carry = 0;            // f entering the first column of the round
+        int hcarry = fc;          // h of the column left of the round
         int key = -1;
-        for (int gbase = j0 & ~(K2_GROUP - 1); gbase <= lim; gbase += K2_GROUP) {
+        for (int rbase = j0 & ~(K2_GROUP - 1); rbase <= lim; rbase += K2_GROUP * K2_WARPS) {
+            const int gbase = rbase + K2_GROUP * warp;
+            const bool active = gbase <= lim;                   // warp-uniform
             const int jl = gbase + 8 * lane;
             const int lo = j0 - jl, hi = lim - jl;              // columns k with lo <= k < hi are cells of this row
             const bool full = (lo <= 0) && (hi >= 8);
-            const uint4 wa = *reinterpret_cast<const uint4*>(eh + jl);
-            const uint4 wb = *reinterpret_cast<const uint4*>(eh + jl + 4);
-            const uint32_t wd[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
-            const uint32_t qw = qs[jl >> 3];
-            const uint32_t x = GENERIC ? qw : (qw ^ trep);
+            uint32_t wd[8];
             int hh[8], fl[8];
-            int run = 0;
-            // pass 1: everything that does not need the incoming F
+            int run = 0, fin0 = 0;
+            if (active) {
+                const uint4 wa = *reinterpret_cast<const uint4*>(eh + jl);
+                const uint4 wb = *reinterpret_cast<const uint4*>(eh + jl + 4);
+                wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
+                const uint32_t qw = qs[jl >> 3];
+                const uint32_t x = GENERIC ? qw : (qw ^ trep);
+                // pass 1: everything that does not need the incoming F
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
-                const int s = k2_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
-                hh[k] = add_max(M, s, e);                                          // sx:1797,1798
-                int g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
-                if (!full && !(k >= lo && k < hi)) g = 0;
-                fl[k] = run;
-                run = add_max(run, -e_ins, g);                                     // sx:1780,1781
-            }
-            // carries across lanes: prefix max of A[l] + 8*e_ins*l
-            int P = run + e8 * lane;
+                for (int k = 0; k < 8; ++k) {
+                    const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
+                    const int s = k2_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
+                    hh[k] = add_max(M, s, e);                                          // sx:1797,1798
+                    int g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
+                    if (!full && !(k >= lo && k < hi)) g = 0;
+                    fl[k] = run;
+                    run = add_max(run, -e_ins, g);                                     // sx:1780,1781
+                }
+                // carries across lanes: prefix max of A[l] + 8*e_ins*l
+                int P = run + e8 * lane;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, P, d);
-                if (lane >= d) P = imax(P, o);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, P, d);
+                    if (lane >= d) P = imax(P, o);
+                }
+                const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
+                fin0 = (lane > 0) ? imax(Pex - e8 * (lane - 1), 0) : 0;    // f entering this lane if the group's carry-in were 0
+                if (lane == 31) xagg[warp] = imax(run, fin0 - e8);         // f leaving the group (zero carry-in)
+            } else if (lane == 31) {
+                xagg[warp] = 0;
             }
-            int Pex = __shfl_up_sync(0xffffffffu, P, 1);
-            int fin = carry - e8 * lane;
-            if (lane > 0) fin = imax(fin, Pex - e8 * (lane - 1));
-            fin = imax(fin, 0);
-            const int fout = imax(run, fin - e8);
-            carry = __shfl_sync(0xffffffffu, fout, 31);
-            // pass 2: fold the carry, finish H, E, key, zero bits
+            __syncthreads();                                               // (1) group aggregates visible
+            // f entering this warp's group: the round's carry and the aggregates of the groups before it
+            int cin = carry - e256 * warp;
+            int cnext = carry - e256 * K2_WARPS;
+#pragma unroll
+            for (int g = 0; g < K2_WARPS; ++g) {
+                const int ag = xagg[g];
+                if (g < warp) cin = imax(cin, ag - e256 * (warp - 1 - g));
+                cnext = imax(cnext, ag - e256 * (K2_WARPS - 1 - g));
+            }
+            cin = imax(cin, 0);
+            carry = imax(cnext, 0);
+
             int h[8];
             uint32_t enew[8];
             uint32_t zbits = 0;
-            int u = fin;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int f = imax(fl[k], u);
-                u -= e_ins;
-                h[k] = imax(hh[k], f);                                             // sx:1809
-                const int t = add_max_relu(h[k], -oe_del, 0);                      // sx:1866,1862
-                enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);   // {max(e-e_del,t), max(M-32768,0)=0}  sx:1770-1771
-                if (full || (k >= lo && k < hi)) {
-                    key = imax(key, h[k] * 65536 + jl + k);                        // sx:1808,1816
-                    zbits |= (h[k] == 0 ? 1u : 0u) << k;
-                }
-            }
-            int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
-            if (lane == 0) hleft = hcarry;
-            hcarry = __shfl_sync(0xffffffffu, h[7], 31);
-            if (full) {
-                // interior lane: columns jl..jl+7 are all cells of this row
-                uint4 oa, ob;
-                oa.x = enew[0] | (uint32_t)((lo == 0) ? fc : hleft);
-                oa.y = enew[1] | (uint32_t)h[0]; oa.z = enew[2] | (uint32_t)h[1]; oa.w = enew[3] | (uint32_t)h[2];
-                ob.x = enew[4] | (uint32_t)h[3]; ob.y = enew[5] | (uint32_t)h[4]; ob.z = enew[6] | (uint32_t)h[5]; ob.w = enew[7] | (uint32_t)h[6];
-                *reinterpret_cast<uint4*>(eh + jl) = oa;
-                *reinterpret_cast<uint4*>(eh + jl + 4) = ob;
-            } else {
-                // boundary lane: store cells [lo,hi) and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
+            if (active) {
+                // pass 2: fold the carry, finish H, E, key, zero bits
+                int u = imax(fin0, cin - e8 * lane);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (k >= lo && k <= hi) {
-                        const int h1 = (k == lo) ? fc : (k ? h[k - 1] : hleft);
-                        eh[jl + k] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
+                    const int f = imax(fl[k], u);
+                    u -= e_ins;
+                    h[k] = imax(hh[k], f);                                             // sx:1809
+                    const int t = add_max_relu(h[k], -oe_del, 0);                      // sx:1866,1862
+                    enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);        // {max(e-e_del,t), max(M-32768,0)=0}  sx:1770-1771
+                    if (full || (k >= lo && k < hi)) {
+                        key = imax(key, h[k] * 65536 + jl + k);                        // sx:1808,1816
+                        zbits |= (h[k] == 0 ? 1u : 0u) << k;
                     }
                 }
+                if (lane == 31) xhl[warp] = h[7];
             }
-            reinterpret_cast<unsigned char*>(zb)[jl >> 3] = (unsigned char)zbits;
+            __syncthreads();                                               // (2) last-column h of every group visible
+            if (active) {
+                int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
+                if (lane == 0) hleft = (warp == 0) ? hcarry : xhl[warp - 1];
+                if (full) {
+                    // interior lane: columns jl..jl+7 are all cells of this row
+                    uint4 oa, ob;
+                    oa.x = enew[0] | (uint32_t)((lo == 0) ? fc : hleft);
+                    oa.y = enew[1] | (uint32_t)h[0]; oa.z = enew[2] | (uint32_t)h[1]; oa.w = enew[3] | (uint32_t)h[2];
+                    ob.x = enew[4] | (uint32_t)h[3]; ob.y = enew[5] | (uint32_t)h[4]; ob.z = enew[6] | (uint32_t)h[5]; ob.w = enew[7] | (uint32_t)h[6];
+                    *reinterpret_cast<uint4*>(eh + jl) = oa;
+                    *reinterpret_cast<uint4*>(eh + jl + 4) = ob;
+                } else {
+                    // boundary lane: store cells [lo,hi) and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k >= lo && k <= hi) {
+                            const int h1 = (k == lo) ? fc : (k ? h[k - 1] : hleft);
+                            eh[jl + k] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
+                        }
+                    }
+                }
+                reinterpret_cast<unsigned char*>(zb)[jl >> 3] = (unsigned char)zbits;
+            }
+            hcarry = xhl[K2_WARPS - 1];          // only consumed when another round follows (then the last warp was active)
         }
-        __syncwarp();
-
-        // ---- row epilogue (warp-uniform) ----
         key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) xkey[warp] = key;
+        __syncthreads();                                                   // (3) row buffer, zero bits and keys visible
+
+        // ---- row epilogue (identical in every thread of the CTA) ----
+        key = imax(imax(xkey[0], xkey[1]), imax(xkey[2], xkey[3]));
         const int m = key >> 16, mj = key & 0xffff;
         cells += (unsigned long long)(lim - j0);
         const int h1 = (int)(eh[lim] & 0xffffu);
@@ -236,10 +269,9 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
         ce = __reduce_min_sync(0xffffffffu, ce);
         beg = cb >= 0 ? cb + 2 : (fc == 0 ? j0 + 1 : j0);
         end = ce != 0x7fffffff ? ce + 1 : lim + 1;
-        __syncwarp();
     }
 
-    if (lane == 0) {
+    if (tid == 0) {
         int4* o = reinterpret_cast<int4*>(A.out + slot);
         const unsigned long long cc = cells > 0x7fffffffull ? 0x7fffffffull : cells;
         o[0] = make_int4(max, max_j + 1, max_i + 1, max_ie + 1);                   // sx:1315-1375 (score,qle,tle,gtle)

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -249,7 +250,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
             const int occ = occupancy(smem);
             if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw; }
             else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = nqw; }      // saturated sort key (very long tasks)
-            else if (occ * 10 >= occ0 * 13) {
+            else if (!is_k2 && occ * 10 >= occ0 * 13) {      // K2: one launch per class (measured: bucket tails cost more than occupancy gains)
                 close_launch(L, (uint32_t)plan->tiles.size());
                 L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw; occ0 = occ;
             }

@@ -221,3 +221,19 @@ def test_full_size_properties(B, O, ctx):
 def test_int_peak_microbenchmark(ctx):
     pk = ctx.measure_int_peak(0)
     assert pk["sm_count"] >= 100 and 5.0 < pk["iadd_tops"] < 80.0 and pk["dpx_tops"] > pk["vimnmx_tops"]
+
+
+def test_multi_device_context_shards_without_collective(B, O):
+    """One context over every visible GPU: chunks are pulled dynamically by workers bound round-robin to the devices."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    t = B.synth_tasks("cfg3_mixed", 200_000, seed=40)
+    p, po = B.make_params(), O.make_params()
+    with B.Context(devices=list(range(ndev)), chunk_tasks=8192) as mctx:
+        assert mctx.num_devices == ndev
+        rg, cg = mctx.sw_extend_batch(p, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    ro, co = O.extend_batch(po, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    assert_same(ro, rg, "multi-device results")
+    assert_same(co, cg.astype(np.int64), "multi-device cells")
