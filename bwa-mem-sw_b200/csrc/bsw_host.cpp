@@ -38,6 +38,8 @@ double now_ms()
 // One staging slot = one in-flight chunk on one stream.
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = { nullptr, nullptr };           // extra streams: the bucket launches of one big plan overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr };
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     // One pinned input block per chunk, mirrored on the device and moved with a single cudaMemcpyAsync:
     //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] ]   (16-byte aligned parts)
@@ -162,6 +164,11 @@ int slot_init(bsw_ctx* ctx, Slot& s)
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k0));
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k1));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s.side[k], cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_join[k], cudaEventDisableTiming));
+    }
     CUDA_TRY(ctx, cudaMalloc((void**)&s.d_cells, sizeof(unsigned long long)));
     CUDA_TRY(ctx, cudaHostAlloc((void**)&s.h_cells, sizeof(unsigned long long), cudaHostAllocDefault));
     return 0;
@@ -179,6 +186,8 @@ void slot_free(Slot& s)
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    for (int k = 0; k < 2; ++k) { if (s.ev_join[k]) cudaEventDestroy(s.ev_join[k]); if (s.side[k]) cudaStreamDestroy(s.side[k]); }
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -221,14 +230,29 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
 {
     const Plan& P = s.plan;
     size_t nl = 0;
+    // A big plan has one launch per occupancy bucket; issued on one stream each bucket would wait for the previous
+    // bucket's last CTA.  Spread them over the slot's three streams (fork after the gather, join before the D2H).
+    const bool spread = P.launches.size() > 1 && P.tiles.size() >= 2048;
+    if (spread) {
+        CUDA_TRY(ctx, cudaEventRecord(s.ev_fork, s.stream));
+        for (int k = 0; k < 2; ++k) CUDA_TRY(ctx, cudaStreamWaitEvent(s.side[k], s.ev_fork, 0));
+    }
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
-        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 1) ? s.d_arena : s.d_src(); a.out = s.d_out;
+        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
-        cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, s.stream)
-                                      : k2_launch(a, L.generic, s.stream);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : "K2 launch");
+        cudaStream_t st = spread ? (nl % 3 == 0 ? s.stream : s.side[nl % 3 - 1]) : s.stream;
+        cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
+                      : (L.kind == 3) ? k1p_launch(a, sym, st)
+                                      : k2_launch(a, L.generic, st);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : (L.kind == 3 ? "K1P launch" : "K2 launch"));
         ++nl;
+    }
+    if (spread) {
+        for (int k = 0; k < 2; ++k) {
+            CUDA_TRY(ctx, cudaEventRecord(s.ev_join[k], s.side[k]));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(s.stream, s.ev_join[k], 0));
+        }
     }
     *nlaunch = nl;
     return 0;
@@ -559,6 +583,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
     else { set_error(ctx, "unknown option " + k); return BSW_EINVAL; }

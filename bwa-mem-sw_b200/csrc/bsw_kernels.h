@@ -13,6 +13,10 @@ cudaError_t k0_launch(const GatherArgs& a, cudaStream_t st);
 cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
 size_t k1_smem_bytes(int qmax, int nqw_max);
 
+// K1P: two tasks per lane, int16x2-packed scores (V1 recurrence, match/mismatch scoring).  a.tiles = (A, B) tile pairs.
+cudaError_t k1p_launch(const LaunchArgs& a, int sym, cudaStream_t st);
+size_t k1p_smem_bytes(int qmax, int nqw_max);
+
 // K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  Variant 1 only.
 cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st);
 size_t k2_smem_bytes(int qmax);

@@ -153,6 +153,10 @@ static inline size_t k1_tile_smem(int qmax, int nqw)
 {
     return 128 + ((size_t)(nqw + 8) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;
 }
+static inline size_t k1p_tile_smem(int qmax, int nqw)
+{
+    return 128 + (size_t)2 * (size_t)(nqw + 8) * TILE_LANES * 4u + (size_t)(qmax + 1 + K1_EH_SLACK) * TILE_LANES * 8u;
+}
 static inline size_t k2_task_smem(int qmax)
 {
     const size_t qcap = ((size_t)qmax + 1 + 255) & ~(size_t)255;
@@ -209,52 +213,60 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
         size_t cend = i;
         while (cend < n && (key[order[cend]] >> 30) == c) ++cend;
         const bool is_k2 = (c & 2u) != 0;
+        const bool is_pair = !is_k2 && (c & 1u) == 0 && opt.pair && opt.variant == 1;
         Launch L{};
-        L.kind = is_k2 ? 2 : 1; L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
+        L.kind = is_k2 ? 2 : (is_pair ? 3 : 1); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
         int occ0 = 0;
         while (i < cend) {
-            TileHdr hd{};
-            hd.slot0 = (uint32_t)plan->slots.size();
-            int qmax = 0, tmax = 0;
-            const size_t ntask = is_k2 ? 1 : std::min<size_t>(TILE_LANES, cend - i);
-            for (size_t k = 0; k < ntask; ++k) {
-                const uint32_t ti = order[i + k];
-                const ExtTask& t = tasks[ti];
-                qmax = std::max(qmax, t.qlen); tmax = std::max(tmax, t.tlen);
-                plan->slots.push_back(SlotParam{ t.qlen, t.tlen, t.h0, t.w });
-                plan->slot_src.push_back(src[ti]);
-                plan->slot_task.push_back((int64_t)ti);
-                const int64_t band = std::min<int64_t>(t.qlen, 2 * (int64_t)t.w + 1);
-                plan->est_cells += (uint64_t)(band * t.tlen);
-            }
-            if (!is_k2)
-                for (size_t k = ntask; k < (size_t)TILE_LANES; ++k) {
-                    plan->slots.push_back(SlotParam{ 0, 0, 0, 0 });
-                    plan->slot_src.push_back(SlotSrc{ 0, 0 });
-                    plan->slot_task.push_back(-1);
+            // one K2 task, one K1 tile of 32 tasks, or one K1P pair of tiles (64 tasks: lane l = tasks 2l and 2l+1)
+            const size_t ntask = is_k2 ? 1 : std::min<size_t>(is_pair ? 2 * TILE_LANES : TILE_LANES, cend - i);
+            const int nsub = is_pair ? 2 : 1;
+            TileHdr hd[2];
+            int qmax = 0, nqw_max = 0;
+            for (int sub = 0; sub < nsub; ++sub) {
+                hd[sub] = TileHdr{};
+                hd[sub].slot0 = (uint32_t)plan->slots.size();
+                int tq = 0, tt = 0;
+                const size_t lanes = is_k2 ? 1 : (size_t)TILE_LANES;
+                for (size_t l = 0; l < lanes; ++l) {
+                    const size_t k = is_pair ? 2 * l + (size_t)sub : l;
+                    if (k < ntask) {
+                        const uint32_t ti = order[i + k];
+                        const ExtTask& t = tasks[ti];
+                        tq = std::max(tq, t.qlen); tt = std::max(tt, t.tlen);
+                        plan->slots.push_back(SlotParam{ t.qlen, t.tlen, t.h0, t.w });
+                        plan->slot_src.push_back(src[ti]);
+                        plan->slot_task.push_back((int64_t)ti);
+                        const int64_t band = std::min<int64_t>(t.qlen, 2 * (int64_t)t.w + 1);
+                        plan->est_cells += (uint64_t)(band * t.tlen);
+                    } else {
+                        plan->slots.push_back(SlotParam{ 0, 0, 0, 0 });
+                        plan->slot_src.push_back(SlotSrc{ 0, 0 });
+                        plan->slot_task.push_back(-1);
+                    }
                 }
-            const int nqw = (qmax + 7) >> 3, ntw = (tmax + 7) >> 3;
-            size_t smem;
-            if (is_k2) {
-                hd.qoff16 = src[order[i]].qoff16;                           // K2 reads the source arena directly
-                hd.toff16 = src[order[i]].toff16;
-                smem = k2_task_smem(qmax);
-            } else {
-                hd.qoff16 = (uint32_t)arena16; arena16 += (size_t)nqw * TILE_LANES * 4 / 16;
-                hd.toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
-                smem = k1_tile_smem(qmax, nqw);
-                ++plan->n_k1_tiles;
+                const int nqw = (tq + 7) >> 3, ntw = (tt + 7) >> 3;
+                if (is_k2) {
+                    hd[sub].qoff16 = src[order[i]].qoff16;                      // K2 reads the source arena directly
+                    hd[sub].toff16 = src[order[i]].toff16;
+                } else {
+                    hd[sub].qoff16 = (uint32_t)arena16; arena16 += (size_t)nqw * TILE_LANES * 4 / 16;
+                    hd[sub].toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
+                    ++plan->n_k1_tiles;
+                }
+                hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+                qmax = std::max(qmax, tq); nqw_max = std::max(nqw_max, nqw);
             }
-            hd.nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+            const size_t smem = is_k2 ? k2_task_smem(qmax) : (is_pair ? k1p_tile_smem(qmax, nqw_max) : k1_tile_smem(qmax, nqw_max));
             // bucket boundary: start a new launch when this tile would fit at >= 1.3x the occupancy of the launch
             const int occ = occupancy(smem);
-            if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw; }
-            else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = nqw; }      // saturated sort key (very long tasks)
+            if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw_max; }
+            else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw_max); }   // saturated sort key (very long tasks)
             else if (!is_k2 && occ * 10 >= occ0 * 13) {      // K2: one launch per class (measured: bucket tails cost more than occupancy gains)
                 close_launch(L, (uint32_t)plan->tiles.size());
-                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw; occ0 = occ;
+                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; occ0 = occ;
             }
-            plan->tiles.push_back(hd);
+            for (int sub = 0; sub < nsub; ++sub) plan->tiles.push_back(hd[sub]);
             i += ntask;
         }
         close_launch(L, (uint32_t)plan->tiles.size());

@@ -31,6 +31,8 @@ struct SchedOptions {
     int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
     int host_threads = 0;       // 0 = hardware concurrency (capped)
     bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
+    bool pair = false;          // V1 + FAST tasks run two per lane (K1P, packed int16x2).  Off by default: measured slower
+                                // than K1 on B200 (occupancy halves with the doubled row buffer), see DESIGN.md section 5
 };
 
 constexpr int K1_QLEN_CAP = 1536;        // shared-memory limit of one K1 tile (227 KB / (32 lanes * 4.5 B per column))
@@ -38,7 +40,7 @@ constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
 constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
 
 struct Launch {
-    int kind;          // 1 = K1, 2 = K2
+    int kind;          // 1 = K1, 2 = K2, 3 = K1P (tiles come in pairs: A tile, B tile)
     int generic;       // 1 = matrix lookup scoring
     uint32_t tile0, ntiles;
     int qmax, nqw_max;

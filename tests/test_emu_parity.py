@@ -69,3 +69,17 @@ def test_rejects_bad_input(B):
     with pytest.raises(B.BswError) as e:
         B.emu_extend_batch(p, qbuf, qoff, tbuf, toff, [10], [100])
     assert e.value.code == B.BSW_ERANGE
+
+
+@pytest.mark.parametrize("name", ["cfg2_150bp", "cfg3_mixed"])
+def test_pair_packed_lane_function(B, O, name):
+    """K1P (two tasks per lane, int16x2-packed scores; bsw_k1p_core.cuh) must give the same answers as K1 and the oracle."""
+    import ctypes as C
+    flag = C.c_int.in_dll(B.emu_lib(), "bsw_emu_pair")
+    flag.value = 1
+    try:
+        run_both(B, O, B.synth_tasks(name, 6000, seed=8))
+        run_both(B, O, B.synth_tasks(name, 3000, seed=9), o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30)
+        run_both(B, O, B.synth_tasks(name, 3000, seed=10, n_frac=0.02))      # N tasks fall back to K1's matrix path
+    finally:
+        flag.value = 0

@@ -237,3 +237,14 @@ def test_multi_device_context_shards_without_collective(B, O):
     ro, co = O.extend_batch(po, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     assert_same(ro, rg, "multi-device results")
     assert_same(co, cg.astype(np.int64), "multi-device cells")
+
+
+def test_k1p_two_tasks_per_lane(B, O, ctx):
+    """Optional K1P kernel (k1_pair=1): int16x2 lanes carrying two tasks each."""
+    ctx.set_option("k1_pair", 1)
+    try:
+        both(B, O, ctx, B.synth_tasks("cfg2_150bp", 40_000, seed=50))
+        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 40_000, seed=51))
+        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=52, n_frac=0.01), o_del=4, e_del=2, o_ins=7, e_ins=1)
+    finally:
+        ctx.set_option("k1_pair", 0)
