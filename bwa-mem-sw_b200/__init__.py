@@ -437,6 +437,7 @@ def emu_lib() -> C.CDLL:
         E = C.CDLL(EMU_PATH)
         vp = C.c_void_p
         E.bsw_emu_extend_batch_flat.argtypes = [C.POINTER(Params), C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp]
+        E.bsw_emu_chain2aln.argtypes = [C.POINTER(Params2), C.c_int, vp, C.c_size_t, vp]
         _emu = E
     return _emu
 
@@ -452,3 +453,14 @@ def emu_extend_batch(params: Params, qbuf, qoff, tbuf, toff, h0, w, variant: int
     if rc != BSW_OK:
         raise BswError(rc, "emulation")
     return out, cells, info
+
+
+def emu_chain2aln(params2: Params2, seeds, variant: int = 1):
+    """TEST ONLY: level 2 through the host scheduler + the K3 lane function compiled for the CPU."""
+    tasks, keep = make_seed_tasks(seeds)
+    out = np.zeros(len(seeds), dtype=ALN_DTYPE)
+    rc = emu_lib().bsw_emu_chain2aln(C.byref(params2), variant, tasks, len(seeds), out.ctypes.data)
+    del keep
+    if rc != BSW_OK:
+        raise BswError(rc, "emulation (level 2)")
+    return out

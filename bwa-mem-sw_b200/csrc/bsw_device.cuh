@@ -48,6 +48,7 @@ struct DevParams {
     int32_t match, mismatch;       // FAST scoring: +match / -mismatch (mismatch stored positive)
     uint32_t row_lo[5], row_hi[5]; // GENERIC scoring: row t of the 5x5 matrix as bytes {s(t,0..3)} / {s(t,4),0,0,0}
     int8_t  mat[28];               // the 5x5 matrix itself (K2 GENERIC lookup), padded
+    int32_t max_mat;               // max entry of the matrix (ksw_extend2's band clamp, used by the fused seed kernel)
     uint32_t zero;                 // always 0: a zero the compiler cannot fold (keeps it in one register, see bsw_k1_core.cuh)
 };
 
@@ -61,6 +62,13 @@ struct GatherArgs {
     uint32_t         ntiles;
 };
 
+// Per-seed scalars of the fused level-2 kernel K3 (one FPGA PE task: sw_pe_array_proc_element.v:1593-1685).
+struct __attribute__((aligned(16))) SeedParam {
+    int32_t init_score, qbeg, h0;  // regScore, qBeg_ori, h0 (param words 3,4: proc_element.v:871-874,826-828)
+    uint32_t id;                   // param word 7 (proc_element.v:807)
+    int32_t max_ins[2], max_del[2];// param words 5,6 when they come from the wire (proc_element.v:924-934); -1 = ksw_extend2's formula
+};
+
 // One kernel launch = tiles [0, ntiles) of `tiles`.
 struct LaunchArgs {
     const TileHdr*   tiles;
@@ -72,6 +80,9 @@ struct LaunchArgs {
     uint32_t         ntiles;
     int32_t          qmax;         // max qlen over the launch (sizes the per-lane row buffer)
     int32_t          nqw_max;      // max query words per lane over the launch (K1)
+    // K3 (fused seed task) only: tiles come in (left, right) pairs, seeds[pair*32 + lane]
+    const SeedParam* seeds;
+    int32_t          w, pen_clip5, pen_clip3;
 };
 
 constexpr int STATUS_OK = 0;

@@ -94,6 +94,7 @@ struct bsw_ctx {
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 32768;
+    bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     bool kernel_timing = true;     // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms)
     std::mutex mu;                 // serialises batch calls on this context
     std::mutex err_mu;
@@ -205,6 +206,7 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
     int mx = 0;
     for (int k = 0; k < 25; ++k) { dp->mat[k] = p->mat[k]; mx = mx > p->mat[k] ? mx : p->mat[k]; }
     *max_mat = mx;
+    dp->max_mat = mx;
     // FAST scoring applies to N-free tasks when the 4x4 core is +a on the diagonal and -b elsewhere
     bool fast = true;
     const int a = p->mat[0], b = -p->mat[1];
@@ -583,6 +585,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
@@ -618,13 +621,10 @@ int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t*
 // (sw_pe_array_proc_element.v:1671,1652), right try 1.  The clip decision (pe:1672-1675) runs on the host.
 #define BSW_MAX_BAND_TRY 2
 
-int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
-                       const bsw_seed_clamp* clamps, bsw_aln_record* out)
+static int chain2aln_host(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
+                          const bsw_seed_clamp* clamps, bsw_aln_record* out)
 {
-    if (!ctx) return BSW_EINVAL;
     if (n == 0) return BSW_OK;
-    if (!P || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
-    if (P->p.e_ins < 1 || P->p.e_del < 1 || P->w < 0) { set_error(ctx, "bad parameters"); return BSW_EINVAL; }
     struct St { int sc0, score, truesc, qb, qe, rb, re, aw[2]; };
     std::vector<St> st(n);
     for (size_t i = 0; i < n; ++i) {                                      // pe:471-475,581-583,...,783-797
@@ -692,6 +692,165 @@ int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* 
         r.id = tasks[i].id; r.qb = S.qb; r.qe = S.qe; r.rb = S.rb; r.re = S.re;
         r.score = S.score; r.truesc = S.truesc; r.w = S.aw[0] > S.aw[1] ? S.aw[0] : S.aw[1];      // pe:1669,1684
     }
+    return BSW_OK;
+}
+
+// ---- level 2, fused on the device (K3): one seed per lane, no host round trip between the two extensions ----
+// Seeds whose flanks do not fit a K1 tile are returned in `leftover` for the host-orchestrated path above.
+static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
+                           const bsw_seed_clamp* clamps, bsw_aln_record* out, std::vector<size_t>* leftover)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
+    int rc = make_dev_params(ctx, &P->p, &dp, &sym, &fast_ok, &max_mat);
+    if (rc) return rc;
+    SchedOptions opt = ctx->opt;
+    opt.fast_matrix = fast_ok; opt.force_kernel = 1;
+    // eligibility / validation
+    std::vector<size_t> elig;
+    elig.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const bsw_seed_task& s = tasks[i];
+        const int ql = s.qlen[0], qr = s.qlen[1];
+        if (ql < 0 || qr < 0 || (ql > 0 && (s.tlen[0] < 1 || s.h0 < 1 || !s.q_left || !s.t_left)) ||
+            (qr > 0 && (s.tlen[1] < 1 || !s.q_right || !s.t_right)) || (ql == 0 && qr > 0 && s.init_score < 1)) {
+            set_error(ctx, "seed task " + std::to_string(i) + ": empty target, h0 < 1 or null flank pointer");
+            return BSW_EINVAL;
+        }
+        const int64_t hmax = (int64_t)std::max(s.h0, s.init_score) + (int64_t)(ql + qr) * max_mat;
+        if (hmax > SCORE_CAP) { set_error(ctx, "seed task " + std::to_string(i) + ": score bound exceeds the 16-bit row state"); return BSW_ERANGE; }
+        if (ql > K1_QLEN_CAP || qr > K1_QLEN_CAP || s.tlen[0] > 500000 || s.tlen[1] > 500000) leftover->push_back(i);
+        else elig.push_back(i);
+    }
+    if (elig.empty()) return BSW_OK;
+    Worker* W = get_worker(ctx, 0);
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)W->dev].id));
+    if (!W->ready) {
+        for (Slot& sl : W->slots) if (!rc) rc = slot_init(ctx, sl);
+        if (rc) { cudaSetDevice(prev_dev); return rc; }
+        W->ready = true;
+    }
+    struct InFlight { size_t first = 0, count = 0; size_t npair_lanes = 0; bool busy = false; };
+    InFlight fl[2];
+    auto collect = [&](int k) -> int {
+        if (!fl[k].busy) return 0;
+        Slot& sl = W->slots[k];
+        CUDA_TRY(ctx, cudaEventSynchronize(sl.ev_done));
+        fl[k].busy = false;
+        const bsw_aln_record* recs = reinterpret_cast<const bsw_aln_record*>(sl.h_out);
+        for (size_t q = 0; q < fl[k].npair_lanes; ++q) {
+            const int64_t sidx = sl.plan.lane_seed[q];
+            if (sidx < 0) continue;
+            out[elig[fl[k].first + (size_t)sidx]] = recs[q];
+        }
+        return 0;
+    };
+    const size_t chunk = 16384;
+    int cur = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    for (size_t first = 0; first < elig.size() && !rc; first += chunk, cur ^= 1) {
+        const size_t cnt = std::min(chunk, elig.size() - first);
+        Slot& sl = W->slots[cur];
+        if ((rc = collect(cur))) break;
+        sl.tasks.resize(2 * cnt); sl.cls.resize(2 * cnt); sl.src.resize(2 * cnt);
+        for (size_t k = 0; k < cnt; ++k) {
+            const bsw_seed_task& s = tasks[elig[first + k]];
+            ExtTask& l = sl.tasks[2 * k]; ExtTask& r = sl.tasks[2 * k + 1];
+            l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
+            r.q = s.q_right; r.t = s.t_right; r.qlen = s.qlen[1]; r.tlen = s.qlen[1] ? s.tlen[1] : 0; r.h0 = s.qlen[1] ? 1 : 0; r.w = s.qlen[1] ? 0 : -2;
+        }
+        const size_t src_bound = source_arena_bound(sl.tasks.data(), 2 * cnt) * 4;
+        const size_t max_slots = 2 * (cnt + 2 * TILE_LANES), max_tiles = max_slots / TILE_LANES + 4;
+        const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc)) +
+                                (max_slots / 2) * sizeof(SeedParam) + 128;
+        if ((rc = grow_pinned(ctx, &sl.h_in, &sl.h_in_cap, in_bound))) break;
+        size_t bad = 0; std::string msg;
+        rc = pack_tasks(sl.tasks.data(), 2 * cnt, max_mat, opt, sl.cls.data(), sl.src.data(), reinterpret_cast<uint32_t*>(sl.h_in),
+                        &sl.src_words, &bad, &msg);
+        if (rc) { set_error(ctx, "seed task " + std::to_string(elig[first + bad / 2]) + (bad & 1 ? " (right flank)" : " (left flank)") + ": invalid base code or length"); break; }
+        build_seed_plan(sl.tasks.data(), sl.cls.data(), sl.src.data(), cnt, opt, &sl.plan);
+        Plan& PL = sl.plan;
+        const size_t nslots = PL.slots.size(), nlanes = PL.lane_seed.size();
+        sl.off_tiles = (sl.src_words * 4 + 15) & ~(size_t)15;
+        sl.off_slots = sl.off_tiles + PL.tiles.size() * sizeof(TileHdr);
+        sl.off_ssrc = sl.off_slots + nslots * sizeof(SlotParam);
+        const size_t off_seeds = (sl.off_ssrc + nslots * sizeof(SlotSrc) + 15) & ~(size_t)15;
+        sl.in_bytes = off_seeds + nlanes * sizeof(SeedParam);
+        if (sl.in_bytes > sl.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); rc = BSW_ENOMEM; break; }
+        if ((rc = grow_pinned(ctx, &sl.h_out, &sl.h_out_cap, nlanes))) break;
+        if ((rc = grow_device(ctx, &sl.d_in, &sl.d_in_cap, in_bound))) break;
+        if ((rc = grow_device(ctx, &sl.d_arena, &sl.d_arena_cap, PL.tiled_words))) break;
+        if ((rc = grow_device(ctx, &sl.d_out, &sl.d_out_cap, nlanes))) break;
+        memcpy(sl.h_in + sl.off_tiles, PL.tiles.data(), PL.tiles.size() * sizeof(TileHdr));
+        memcpy(sl.h_in + sl.off_slots, PL.slots.data(), nslots * sizeof(SlotParam));
+        memcpy(sl.h_in + sl.off_ssrc, PL.slot_src.data(), nslots * sizeof(SlotSrc));
+        SeedParam* sp = reinterpret_cast<SeedParam*>(sl.h_in + off_seeds);
+        for (size_t q = 0; q < nlanes; ++q) {
+            const int64_t sidx = PL.lane_seed[q];
+            SeedParam& d = sp[q];
+            if (sidx < 0) { d = SeedParam{ 0, 0, -1, 0, { -1, -1 }, { -1, -1 } }; continue; }
+            const size_t gi = elig[first + (size_t)sidx];
+            const bsw_seed_task& s = tasks[gi];
+            d.init_score = s.init_score; d.qbeg = s.qbeg; d.h0 = s.h0 > 0 ? s.h0 : 0; d.id = s.id;
+            for (int side = 0; side < 2; ++side) {
+                d.max_ins[side] = clamps ? clamps[gi].max_ins[side] : -1;
+                d.max_del[side] = clamps ? clamps[gi].max_del[side] : -1;
+            }
+        }
+        cudaError_t ce = cudaMemcpyAsync(sl.d_in, sl.h_in, sl.in_bytes, cudaMemcpyHostToDevice, sl.stream);
+        if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "level-2 H2D"); break; }
+        if ((rc = enqueue_gather(ctx, sl))) break;
+        for (const Launch& L : PL.launches) {
+            LaunchArgs a{};
+            a.tiles = sl.d_tiles() + L.tile0; a.slots = sl.d_slots(); a.arena = sl.d_arena;
+            a.out = sl.d_out + (size_t)(L.tile0 / 2) * TILE_LANES;
+            a.cells_total = nullptr; a.p = dp; a.p.max_mat = max_mat; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+            a.seeds = reinterpret_cast<const SeedParam*>(sl.d_in + off_seeds) + (size_t)(L.tile0 / 2) * TILE_LANES;
+            a.w = P->w; a.pen_clip5 = P->pen_clip5; a.pen_clip3 = P->pen_clip3;
+            ce = k3_launch(a, opt.variant, L.generic, sym, sl.stream);
+            if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "K3 launch"); break; }
+            ++launches;
+        }
+        if (rc) break;
+        ce = cudaMemcpyAsync(sl.h_out, sl.d_out, nlanes * sizeof(SlotResult), cudaMemcpyDeviceToHost, sl.stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(sl.ev_done, sl.stream);
+        if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "level-2 D2H"); break; }
+        fl[cur].first = first; fl[cur].count = cnt; fl[cur].npair_lanes = nlanes; fl[cur].busy = true;
+        ++launches; h2d += sl.in_bytes; d2h += nlanes * sizeof(SlotResult);
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (rc) { if (W->slots[k].stream) cudaStreamSynchronize(W->slots[k].stream); fl[k].busy = false; }
+        else rc = collect(k);
+    }
+    cudaSetDevice(prev_dev);
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->stats.kernel_launches += launches; ctx->stats.h2d_bytes += h2d; ctx->stats.d2h_bytes += d2h;
+    }
+    return rc;
+}
+
+int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
+                       const bsw_seed_clamp* clamps, bsw_aln_record* out)
+{
+    if (!ctx) return BSW_EINVAL;
+    if (n == 0) return BSW_OK;
+    if (!P || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (P->p.e_ins < 1 || P->p.e_del < 1 || P->w < 0) { set_error(ctx, "bad parameters"); return BSW_EINVAL; }
+    if (!ctx->fused_l2) return chain2aln_host(ctx, P, tasks, n, clamps, out);
+    std::vector<size_t> leftover;
+    int rc = chain2aln_fused(ctx, P, tasks, n, clamps, out, &leftover);
+    if (rc || leftover.empty()) return rc;
+    // flanks longer than a K1 tile: host-orchestrated passes (K2 does the long extensions)
+    std::vector<bsw_seed_task> lt(leftover.size());
+    std::vector<bsw_seed_clamp> lc(clamps ? leftover.size() : 0);
+    std::vector<bsw_aln_record> lo(leftover.size());
+    for (size_t k = 0; k < leftover.size(); ++k) { lt[k] = tasks[leftover[k]]; if (clamps) lc[k] = clamps[leftover[k]]; }
+    rc = chain2aln_host(ctx, P, lt.data(), lt.size(), clamps ? lc.data() : nullptr, lo.data());
+    if (rc) return rc;
+    for (size_t k = 0; k < leftover.size(); ++k) out[leftover[k]] = lo[k];
     return BSW_OK;
 }
 

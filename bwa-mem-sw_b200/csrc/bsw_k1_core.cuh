@@ -157,7 +157,7 @@ BSW_HD int k1_lookup(uint32_t nib, uint32_t rlo, uint32_t rhi)
 // words of this lane and has room for nqw_max + K1_QS_EXTRA words.
 template <int VARIANT, int GENERIC, int SYM>
 BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const int h0, const int w, const int nqw_tile,
-                    uint32_t* eh, uint32_t* qs, const uint32_t* tg, SlotResult& res)
+                    uint32_t* eh, uint32_t* qs, const uint32_t* tg, SlotResult& res, const bool prep = true)
 {
     constexpr bool ONEHOT = (VARIANT == 1 && GENERIC == 0);     // the branch-free path of the +a/-b scoring
     const int o_del = P.o_del, e_del = P.e_del, e_ins = P.e_ins;
@@ -182,7 +182,9 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     asm volatile("" : "+r"(mul[0]), "+r"(mul[1]), "+r"(mul[2]), "+r"(mul[3]), "+r"(mul[4]), "+r"(mul[5]), "+r"(mul[6]), "+r"(mul[7]));
 #endif
 
-    if (ONEHOT) {
+    if (!prep) {
+        // the query was prepared by an earlier call on the same lane (band retry of the fused seed kernel)
+    } else if (ONEHOT) {
         // Re-code the query in place: per 32 columns, four words = the positions of A, C, G, T.  A chunk's match bits
         // for target base t are then one funnel shift of plane t (the RTL's mux_25to1 becomes a bit test).
         const int nblk = ((qlen + 31) >> 5) + 1;                 // one all-zero block past the end for the funnel shift

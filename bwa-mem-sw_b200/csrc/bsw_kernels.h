@@ -17,6 +17,11 @@ size_t k1_smem_bytes(int qmax, int nqw_max);
 cudaError_t k1p_launch(const LaunchArgs& a, int sym, cudaStream_t st);
 size_t k1p_smem_bytes(int qmax, int nqw_max);
 
+// K3: fused seed-task kernel (level 2 on the device): left + right extension, band retry, clip, record.
+// a.tiles = (left, right) tile pairs, a.seeds[pair*32+lane], a.out[pair*32+lane] = bsw_aln_record.
+cudaError_t k3_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
+size_t k3_smem_bytes(int qmax, int nqw_max);
+
 // K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  Variant 1 only.
 cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st);
 size_t k2_smem_bytes(int qmax);

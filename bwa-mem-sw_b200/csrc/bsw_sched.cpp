@@ -114,6 +114,7 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
     size_t w = 0;                                       // next free word (multiple of 4)
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& t = tasks[i];
+        if (t.qlen == 0 && t.w == -2) { cls[i] = 0x80; src[i] = SlotSrc{ 0, 0 }; continue; }     // absent flank of a seed task
         int e = 0;
         if (!t.q || !t.t || t.qlen < 1 || t.tlen < 1 || t.h0 < 1 || t.w < 0) e = BSW_EINVAL;
         else if ((int64_t)t.h0 + (int64_t)t.qlen * max_mat > SCORE_CAP || t.qlen > K2_QLEN_CAP || t.tlen > 500000) e = BSW_ERANGE;
@@ -268,6 +269,97 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
             }
             for (int sub = 0; sub < nsub; ++sub) plan->tiles.push_back(hd[sub]);
             i += ntask;
+        }
+        close_launch(L, (uint32_t)plan->tiles.size());
+    }
+    plan->tiled_words = arena16 * 4 + 32;
+}
+
+static inline size_t k3_tile_smem(int qmax, int nqw)
+{
+    return 128 + ((size_t)2 * (size_t)(nqw + 8) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;
+}
+
+void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t nseeds, const SchedOptions& opt, Plan* plan)
+{
+    (void)opt;
+    plan->tiles.clear(); plan->slots.clear(); plan->slot_src.clear(); plan->slot_task.clear(); plan->launches.clear();
+    plan->lane_seed.clear();
+    plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
+    if (nseeds == 0) return;
+    const size_t n = nseeds;
+    std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
+    std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
+    key.resize(n); order.resize(n); tmp.resize(n); hist.assign(65537, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const ExtTask& l = tasks[2 * i]; const ExtTask& r = tasks[2 * i + 1];
+        const uint32_t g = ((cls[2 * i] | cls[2 * i + 1]) & 1u);
+        const uint32_t ql = (uint32_t)std::min(std::max(l.qlen, r.qlen), 16383);
+        const uint32_t qs = (uint32_t)std::min((l.qlen + r.qlen) >> 1, 1023), h = (uint32_t)std::min(l.h0 >> 1, 63);
+        key[i] = (g << 30) | ((16383u - ql) << 16) | ((1023u - qs) << 6) | (63u - h);
+    }
+    for (size_t i = 0; i < n; ++i) ++hist[(key[i] & 0xffffu) + 1];
+    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
+    for (size_t i = 0; i < n; ++i) tmp[hist[key[i] & 0xffffu]++] = (uint32_t)i;
+    hist.assign(65537, 0);
+    for (size_t i = 0; i < n; ++i) ++hist[(key[i] >> 16) + 1];
+    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
+    for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[hist[key[t] >> 16]++] = t; }
+
+    size_t arena16 = 0;
+    auto close_launch = [&](Launch& L, uint32_t tile_end) {
+        L.ntiles = tile_end - L.tile0;
+        if (L.ntiles) plan->launches.push_back(L);
+    };
+    size_t i = 0;
+    while (i < n) {
+        const uint32_t g = key[order[i]] >> 30;
+        size_t cend = i;
+        while (cend < n && (key[order[cend]] >> 30) == g) ++cend;
+        Launch L{};
+        L.kind = 5; L.generic = (int)g; L.tile0 = (uint32_t)plan->tiles.size();
+        int occ0 = 0;
+        while (i < cend) {
+            const size_t ns = std::min<size_t>(TILE_LANES, cend - i);
+            TileHdr hd[2];
+            int qmax = 0, nqw_max = 0;
+            for (int side = 0; side < 2; ++side) {
+                hd[side] = TileHdr{};
+                hd[side].slot0 = (uint32_t)plan->slots.size();
+                int tq = 0, tt = 0;
+                for (size_t l = 0; l < (size_t)TILE_LANES; ++l) {
+                    if (l < ns) {
+                        const size_t ti = 2 * (size_t)order[i + l] + (size_t)side;
+                        const ExtTask& t = tasks[ti];
+                        tq = std::max(tq, t.qlen); tt = std::max(tt, t.qlen > 0 ? t.tlen : 0);
+                        plan->slots.push_back(SlotParam{ t.qlen, t.qlen > 0 ? t.tlen : 0, t.h0, 0 });
+                        plan->slot_src.push_back(src[ti]);
+                        plan->slot_task.push_back((int64_t)ti);
+                        plan->est_cells += (uint64_t)t.qlen * (uint64_t)(t.qlen > 0 ? t.tlen : 0);
+                        if (side == 0) plan->lane_seed.push_back((int64_t)order[i + l]);
+                    } else {
+                        plan->slots.push_back(SlotParam{ 0, 0, 0, 0 });
+                        plan->slot_src.push_back(SlotSrc{ 0, 0 });
+                        plan->slot_task.push_back(-1);
+                        if (side == 0) plan->lane_seed.push_back(-1);
+                    }
+                }
+                const int nqw = (tq + 7) >> 3, ntw = (tt + 7) >> 3;
+                hd[side].qoff16 = (uint32_t)arena16; arena16 += (size_t)nqw * TILE_LANES * 4 / 16;
+                hd[side].toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
+                hd[side].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+                ++plan->n_k1_tiles;
+                qmax = std::max(qmax, tq); nqw_max = std::max(nqw_max, nqw);
+            }
+            const int occ = occupancy(k3_tile_smem(qmax, nqw_max));
+            if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw_max; }
+            else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw_max); }
+            else if (occ * 10 >= occ0 * 13) {
+                close_launch(L, (uint32_t)plan->tiles.size());
+                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; occ0 = occ;
+            }
+            plan->tiles.push_back(hd[0]); plan->tiles.push_back(hd[1]);
+            i += ns;
         }
         close_launch(L, (uint32_t)plan->tiles.size());
     }

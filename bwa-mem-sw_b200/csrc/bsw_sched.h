@@ -40,7 +40,7 @@ constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
 constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
 
 struct Launch {
-    int kind;          // 1 = K1, 2 = K2, 3 = K1P (tiles come in pairs: A tile, B tile)
+    int kind;          // 1 = K1, 2 = K2, 3 = K1P (tiles come in pairs: A tile, B tile), 5 = K3 (pairs: left tile, right tile)
     int generic;       // 1 = matrix lookup scoring
     uint32_t tile0, ntiles;
     int qmax, nqw_max;
@@ -57,6 +57,8 @@ struct Plan {
     uint64_t est_cells = 0;
     // scratch reused across calls (radix sort of the chunk)
     std::vector<uint32_t> key, order, tmp, hist;
+    // K3 plans: seed index of every (tile pair, lane), -1 = padding lane
+    std::vector<int64_t> lane_seed;
 };
 
 // Upper bound of the source arena for these tasks, in u32 words (16-byte aligned sequences + slack).
@@ -67,6 +69,10 @@ size_t source_arena_bound(const ExtTask* tasks, size_t n);
 // Returns 0 or a negative BSW_E* code; on error *bad_task is the first offending task and msg explains.
 int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
+
+// Level-2 plan: tasks[2*s] / tasks[2*s+1] are the left / right flank of seed s (qlen == 0: absent, cls 0x80).  Seeds are
+// sorted by their longer flank and cut into pairs of K1 tiles (left flanks, right flanks), 32 seeds per pair.
+void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t nseeds, const SchedOptions& opt, Plan* plan);
 
 // Sort, tile, bucket.  Single-threaded: the driver runs one plan per chunk per host thread.
 void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t n, const SchedOptions& opt, Plan* plan);

@@ -15,6 +15,7 @@
 #include "bsw_device.cuh"
 #include "bsw_k1_core.cuh"
 #include "bsw_k1p_core.cuh"
+#include "bsw_k3_core.cuh"
 #include "bsw_sched.h"
 
 using namespace bsw;
@@ -209,4 +210,95 @@ extern "C" int bsw_emu_host_phases(const bsw_params* params, const uint8_t* qbuf
     ms[4] = now() - w0;
     for (int k = 0; k < 4; ++k) { ms[k] = 0; for (int t = 0; t < threads; ++t) ms[k] += sc[(size_t)t].t[k]; }
     return 0;
+}
+
+// Level 2 on the CPU: the host half of bsw_chain2aln_batch's fused path (pack, seed plan, gather) + the K3 lane function.
+namespace {
+template <int VARIANT, int GENERIC, int SYM>
+void run_seed_pair(const DevParams& dp, int w, int pc5, int pc3, const TileHdr& hl, const TileHdr& hr, const SlotParam* slots,
+                   const SeedParam* seeds, const uint32_t* arena, SeedRecord* out, int qmax, int nqw_max)
+{
+    const int nql = (int)(hl.nqw_ntw & 0xffffu), nqr = (int)(hr.nqw_ntw & 0xffffu);
+    const size_t qwords = (size_t)(nqw_max + K1_QS_EXTRA) * K1_S;
+    std::vector<uint32_t> qsl(qwords, 0xdeadbeefu), qsr(qwords, 0xdeadbeefu);
+    std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1_S, 0xdeadbeefu);
+    memcpy(qsl.data(), arena + (size_t)hl.qoff16 * 4, (size_t)nql * K1_S * 4);
+    memcpy(qsr.data(), arena + (size_t)hr.qoff16 * 4, (size_t)nqr * K1_S * 4);
+    for (int lane = 0; lane < K1_S; ++lane) {
+        if (seeds[lane].h0 < 0) continue;
+        uint32_t cells = 0;
+        k3_seed<VARIANT, GENERIC, SYM>(dp, w, pc5, pc3, slots[hl.slot0 + lane], slots[hr.slot0 + lane], seeds[lane], nql, nqr,
+                                       eh.data() + lane, qsl.data() + lane, qsr.data() + lane,
+                                       arena + (size_t)hl.toff16 * 4 + lane, arena + (size_t)hr.toff16 * 4 + lane, out[lane], cells);
+    }
+}
+}  // namespace
+
+extern "C" int bsw_emu_chain2aln(const bsw_params2* P2, int variant, const bsw_seed_task* tasks, size_t n, bsw_aln_record* out)
+{
+    const bsw_params* params = &P2->p;
+    if (params->e_ins < 1 || params->e_del < 1 || params->o_ins < 0 || params->o_del < 0) return BSW_EINVAL;
+    DevParams dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.o_del = params->o_del; dp.e_del = params->e_del; dp.o_ins = params->o_ins; dp.e_ins = params->e_ins; dp.zdrop = params->zdrop;
+    int mx = 0;
+    for (int k = 0; k < 25; ++k) { dp.mat[k] = params->mat[k]; mx = mx > params->mat[k] ? mx : params->mat[k]; }
+    dp.max_mat = mx;
+    bool fast = true;
+    const int a = params->mat[0], b = -params->mat[1];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (params->mat[5 * i + j] != (i == j ? a : -b)) fast = false;
+    dp.match = a; dp.mismatch = b;
+    for (int t = 0; t < 5; ++t) {
+        uint32_t lo = 0;
+        for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)params->mat[5 * t + q] << (8 * q);
+        dp.row_lo[t] = lo; dp.row_hi[t] = (uint32_t)(uint8_t)params->mat[5 * t + 4];
+    }
+    const int sym = (params->o_del == params->o_ins && params->e_del == params->e_ins) ? 1 : 0;
+    SchedOptions opt;
+    opt.variant = variant; opt.force_kernel = 1; opt.fast_matrix = fast; opt.host_threads = 1;
+    std::vector<ExtTask> v(2 * n);
+    for (size_t k = 0; k < n; ++k) {
+        const bsw_seed_task& s = tasks[k];
+        ExtTask& l = v[2 * k]; ExtTask& r = v[2 * k + 1];
+        l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
+        r.q = s.q_right; r.t = s.t_right; r.qlen = s.qlen[1]; r.tlen = s.qlen[1] ? s.tlen[1] : 0; r.h0 = s.qlen[1] ? 1 : 0; r.w = s.qlen[1] ? 0 : -2;
+    }
+    std::vector<uint8_t> cls(2 * n);
+    std::vector<SlotSrc> ssrc(2 * n);
+    std::vector<uint32_t> src(source_arena_bound(v.data(), 2 * n), 0xdeadbeefu);
+    size_t bad = 0, used = 0; std::string msg;
+    int rc = pack_tasks(v.data(), 2 * n, mx, opt, cls.data(), ssrc.data(), src.data(), &used, &bad, &msg);
+    if (rc) return rc;
+    Plan P;
+    build_seed_plan(v.data(), cls.data(), ssrc.data(), n, opt, &P);
+    std::vector<uint32_t> arena(P.tiled_words + 64, 0xdeadbeefu);
+    gather_host(P, src.data(), arena.data());
+    std::vector<SeedParam> sp(P.lane_seed.size());
+    for (size_t q = 0; q < sp.size(); ++q) {
+        const int64_t si = P.lane_seed[q];
+        if (si < 0) { sp[q] = SeedParam{ 0, 0, -1, 0, { -1, -1 }, { -1, -1 } }; continue; }
+        const bsw_seed_task& s = tasks[si];
+        sp[q] = SeedParam{ s.init_score, s.qbeg, s.h0 > 0 ? s.h0 : 0, s.id, { -1, -1 }, { -1, -1 } };
+    }
+    std::vector<SeedRecord> rec(P.lane_seed.size());
+    for (const Launch& L : P.launches) {
+        if (L.kind != 5) return BSW_ERANGE;
+        for (uint32_t t = L.tile0; t + 1 < L.tile0 + L.ntiles; t += 2) {
+            const size_t base = (size_t)(t / 2) * K1_S;
+#define EMU_CASE(V, G, S) if (variant == V && L.generic == G && sym == S) run_seed_pair<V, G, S>(dp, P2->w, P2->pen_clip5, P2->pen_clip3, P.tiles[t], P.tiles[t + 1], P.slots.data(), sp.data() + base, arena.data(), rec.data() + base, L.qmax, L.nqw_max);
+            EMU_CASE(1, 0, 1) EMU_CASE(1, 0, 0) EMU_CASE(1, 1, 1) EMU_CASE(1, 1, 0)
+            EMU_CASE(2, 0, 1) EMU_CASE(2, 0, 0) EMU_CASE(2, 1, 1) EMU_CASE(2, 1, 0)
+#undef EMU_CASE
+        }
+    }
+    for (size_t q = 0; q < rec.size(); ++q) {
+        const int64_t si = P.lane_seed[q];
+        if (si < 0) continue;
+        const SeedRecord& r = rec[q];
+        bsw_aln_record& o = out[si];
+        o.id = r.id; o.qb = r.qb; o.qe = r.qe; o.rb = r.rb; o.re = r.re; o.score = r.score; o.truesc = r.truesc; o.w = r.w;
+    }
+    return BSW_OK;
 }

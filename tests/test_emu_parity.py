@@ -83,3 +83,17 @@ def test_pair_packed_lane_function(B, O, name):
         run_both(B, O, B.synth_tasks(name, 3000, seed=10, n_frac=0.02))      # N tasks fall back to K1's matrix path
     finally:
         flag.value = 0
+
+
+@pytest.mark.parametrize("w,zdrop,variant", [(100, 100, 1), (10, 100, 1), (5, 0, 1), (100, 100, 2), (7, 50, 2)])
+def test_fused_seed_task_lane_function(B, O, w, zdrop, variant):
+    """K3 (bsw_k3_core.cuh): left + right extension, band retry, clip decision per lane == the oracle's chain2aln."""
+    from helpers import oracle_chain2aln, seeds_from_flat
+    t = B.synth_tasks("cfg3_mixed", 3000, seed=60 + w, n_frac=0.005)
+    seeds = seeds_from_flat(t, 1500, unset_score_every=3)
+    P2 = B.make_params2(B.make_params(zdrop=zdrop), w=w, pen_clip5=5, pen_clip3=7)
+    want, _ = oracle_chain2aln(O, B, P2, seeds, variant=variant)
+    got = B.emu_chain2aln(P2, seeds, variant=variant)
+    assert_same(want, got, "fused seed task")
+    if w < 100:
+        assert (want["w"] == 2 * w).any()          # the band-retry path ran

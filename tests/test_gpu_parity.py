@@ -248,3 +248,25 @@ def test_k1p_two_tasks_per_lane(B, O, ctx):
         both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=52, n_frac=0.01), o_del=4, e_del=2, o_ins=7, e_ins=1)
     finally:
         ctx.set_option("k1_pair", 0)
+
+
+def test_level2_host_orchestrated_and_long_flanks(B, O, ctx):
+    """fused_l2=0 (four level-1 passes) gives the same records; seeds with a flank beyond a K1 tile take that path anyway."""
+    t = B.synth_tasks("cfg3_mixed", 2000, seed=70)
+    seeds = seeds_from_flat(t, 1000, unset_score_every=3)
+    lt = B.synth_tasks("cfg4_long", 8, seed=71)                    # 4 seeds with 1-10 kb flanks
+    for r in range(4):
+        l, g = 2 * r, 2 * r + 1
+        seeds.append(dict(q_left=lt["qbuf"][lt["qoff"][l]:lt["qoff"][l + 1]], t_left=lt["tbuf"][lt["toff"][l]:lt["toff"][l + 1]],
+                          q_right=lt["qbuf"][lt["qoff"][g]:lt["qoff"][g + 1]], t_right=lt["tbuf"][lt["toff"][g]:lt["toff"][g + 1]],
+                          init_score=-1, qbeg=int(lt["qoff"][l + 1] - lt["qoff"][l]), h0=int(lt["h0"][l]), id=9000 + r))
+    P2 = B.make_params2(B.make_params(zdrop=100), w=100, pen_clip5=5, pen_clip3=5)
+    want, _ = oracle_chain2aln(O, B, P2, seeds)
+    got = ctx.proc_element_batch(P2, seeds)
+    assert_same(want, got, "fused + leftover")
+    ctx.set_option("fused_l2", 0)
+    try:
+        got2 = ctx.proc_element_batch(P2, seeds)
+    finally:
+        ctx.set_option("fused_l2", 1)
+    assert_same(want, got2, "host-orchestrated")
