@@ -723,53 +723,56 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         else elig.push_back(i);
     }
     if (elig.empty()) return BSW_OK;
-    Worker* W = get_worker(ctx, 0);
-    int prev_dev = 0;
-    cudaGetDevice(&prev_dev);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[(size_t)W->dev].id));
-    if (!W->ready) {
-        for (Slot& sl : W->slots) if (!rc) rc = slot_init(ctx, sl);
-        if (rc) { cudaSetDevice(prev_dev); return rc; }
-        W->ready = true;
-    }
-    struct InFlight { size_t first = 0, count = 0; size_t npair_lanes = 0; bool busy = false; };
-    InFlight fl[2];
-    auto collect = [&](int k) -> int {
-        if (!fl[k].busy) return 0;
-        Slot& sl = W->slots[k];
+    if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
+
+    // the same worker-pipeline structure as run_extensions: chunks of seeds pulled from a shared counter, every worker
+    // packs / plans / submits on its own two stream slots
+    const size_t chunk = 8192;
+    const size_t nchunks = (elig.size() + chunk - 1) / chunk;
+    const size_t ndev = ctx->devs.size();
+    size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
+    if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
+    if (nworkers < 1) nworkers = 1;
+    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
+    std::atomic<size_t> next(0);
+    std::atomic<int> first_err(0);
+    std::atomic<uint64_t> launches(0), h2d(0), d2h(0);
+
+    auto collect = [&](Slot& sl) -> int {
+        if (!sl.busy) return 0;
         CUDA_TRY(ctx, cudaEventSynchronize(sl.ev_done));
-        fl[k].busy = false;
+        sl.busy = false;
         const bsw_aln_record* recs = reinterpret_cast<const bsw_aln_record*>(sl.h_out);
-        for (size_t q = 0; q < fl[k].npair_lanes; ++q) {
+        const size_t nlanes = sl.plan.lane_seed.size();
+        for (size_t q = 0; q < nlanes; ++q) {
             const int64_t sidx = sl.plan.lane_seed[q];
             if (sidx < 0) continue;
-            out[elig[fl[k].first + (size_t)sidx]] = recs[q];
+            out[elig[sl.first + (size_t)sidx]] = recs[q];
         }
         return 0;
     };
-    const size_t chunk = 16384;
-    int cur = 0;
-    uint64_t launches = 0, h2d = 0, d2h = 0;
-    for (size_t first = 0; first < elig.size() && !rc; first += chunk, cur ^= 1) {
-        const size_t cnt = std::min(chunk, elig.size() - first);
-        Slot& sl = W->slots[cur];
-        if ((rc = collect(cur))) break;
+    auto submit = [&](Slot& sl, size_t first, size_t cnt) -> int {
+        int r = 0;
         sl.tasks.resize(2 * cnt); sl.cls.resize(2 * cnt); sl.src.resize(2 * cnt);
         for (size_t k = 0; k < cnt; ++k) {
             const bsw_seed_task& s = tasks[elig[first + k]];
-            ExtTask& l = sl.tasks[2 * k]; ExtTask& r = sl.tasks[2 * k + 1];
+            ExtTask& l = sl.tasks[2 * k]; ExtTask& rr = sl.tasks[2 * k + 1];
             l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
-            r.q = s.q_right; r.t = s.t_right; r.qlen = s.qlen[1]; r.tlen = s.qlen[1] ? s.tlen[1] : 0; r.h0 = s.qlen[1] ? 1 : 0; r.w = s.qlen[1] ? 0 : -2;
+            rr.q = s.q_right; rr.t = s.t_right; rr.qlen = s.qlen[1]; rr.tlen = s.qlen[1] ? s.tlen[1] : 0; rr.h0 = s.qlen[1] ? 1 : 0; rr.w = s.qlen[1] ? 0 : -2;
         }
         const size_t src_bound = source_arena_bound(sl.tasks.data(), 2 * cnt) * 4;
         const size_t max_slots = 2 * (cnt + 2 * TILE_LANES), max_tiles = max_slots / TILE_LANES + 4;
         const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc)) +
                                 (max_slots / 2) * sizeof(SeedParam) + 128;
-        if ((rc = grow_pinned(ctx, &sl.h_in, &sl.h_in_cap, in_bound))) break;
+        if ((r = grow_pinned(ctx, &sl.h_in, &sl.h_in_cap, in_bound))) return r;
         size_t bad = 0; std::string msg;
-        rc = pack_tasks(sl.tasks.data(), 2 * cnt, max_mat, opt, sl.cls.data(), sl.src.data(), reinterpret_cast<uint32_t*>(sl.h_in),
-                        &sl.src_words, &bad, &msg);
-        if (rc) { set_error(ctx, "seed task " + std::to_string(elig[first + bad / 2]) + (bad & 1 ? " (right flank)" : " (left flank)") + ": invalid base code or length"); break; }
+        r = pack_tasks(sl.tasks.data(), 2 * cnt, max_mat, opt, sl.cls.data(), sl.src.data(), reinterpret_cast<uint32_t*>(sl.h_in),
+                       &sl.src_words, &bad, &msg);
+        if (r) {
+            set_error(ctx, "seed task " + std::to_string(elig[first + bad / 2]) + (bad & 1 ? " (right flank)" : " (left flank)") +
+                               ": invalid base code or length");
+            return r;
+        }
         build_seed_plan(sl.tasks.data(), sl.cls.data(), sl.src.data(), cnt, opt, &sl.plan);
         Plan& PL = sl.plan;
         const size_t nslots = PL.slots.size(), nlanes = PL.lane_seed.size();
@@ -778,11 +781,11 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         sl.off_ssrc = sl.off_slots + nslots * sizeof(SlotParam);
         const size_t off_seeds = (sl.off_ssrc + nslots * sizeof(SlotSrc) + 15) & ~(size_t)15;
         sl.in_bytes = off_seeds + nlanes * sizeof(SeedParam);
-        if (sl.in_bytes > sl.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); rc = BSW_ENOMEM; break; }
-        if ((rc = grow_pinned(ctx, &sl.h_out, &sl.h_out_cap, nlanes))) break;
-        if ((rc = grow_device(ctx, &sl.d_in, &sl.d_in_cap, in_bound))) break;
-        if ((rc = grow_device(ctx, &sl.d_arena, &sl.d_arena_cap, PL.tiled_words))) break;
-        if ((rc = grow_device(ctx, &sl.d_out, &sl.d_out_cap, nlanes))) break;
+        if (sl.in_bytes > sl.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); return BSW_ENOMEM; }
+        if ((r = grow_pinned(ctx, &sl.h_out, &sl.h_out_cap, nlanes))) return r;
+        if ((r = grow_device(ctx, &sl.d_in, &sl.d_in_cap, in_bound))) return r;
+        if ((r = grow_device(ctx, &sl.d_arena, &sl.d_arena_cap, PL.tiled_words))) return r;
+        if ((r = grow_device(ctx, &sl.d_out, &sl.d_out_cap, nlanes))) return r;
         memcpy(sl.h_in + sl.off_tiles, PL.tiles.data(), PL.tiles.size() * sizeof(TileHdr));
         memcpy(sl.h_in + sl.off_slots, PL.slots.data(), nslots * sizeof(SlotParam));
         memcpy(sl.h_in + sl.off_ssrc, PL.slot_src.data(), nslots * sizeof(SlotSrc));
@@ -799,37 +802,71 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
                 d.max_del[side] = clamps ? clamps[gi].max_del[side] : -1;
             }
         }
-        cudaError_t ce = cudaMemcpyAsync(sl.d_in, sl.h_in, sl.in_bytes, cudaMemcpyHostToDevice, sl.stream);
-        if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "level-2 H2D"); break; }
-        if ((rc = enqueue_gather(ctx, sl))) break;
+        CUDA_TRY(ctx, cudaMemcpyAsync(sl.d_in, sl.h_in, sl.in_bytes, cudaMemcpyHostToDevice, sl.stream));
+        if ((r = enqueue_gather(ctx, sl))) return r;
+        uint64_t nl = 1;
         for (const Launch& L : PL.launches) {
             LaunchArgs a{};
             a.tiles = sl.d_tiles() + L.tile0; a.slots = sl.d_slots(); a.arena = sl.d_arena;
             a.out = sl.d_out + (size_t)(L.tile0 / 2) * TILE_LANES;
-            a.cells_total = nullptr; a.p = dp; a.p.max_mat = max_mat; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+            a.cells_total = nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
             a.seeds = reinterpret_cast<const SeedParam*>(sl.d_in + off_seeds) + (size_t)(L.tile0 / 2) * TILE_LANES;
             a.w = P->w; a.pen_clip5 = P->pen_clip5; a.pen_clip3 = P->pen_clip3;
-            ce = k3_launch(a, opt.variant, L.generic, sym, sl.stream);
-            if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "K3 launch"); break; }
-            ++launches;
+            cudaError_t ce = k3_launch(a, opt.variant, L.generic, sym, sl.stream);
+            if (ce != cudaSuccess) return cuda_fail(ctx, ce, "K3 launch");
+            ++nl;
         }
-        if (rc) break;
-        ce = cudaMemcpyAsync(sl.h_out, sl.d_out, nlanes * sizeof(SlotResult), cudaMemcpyDeviceToHost, sl.stream);
-        if (ce == cudaSuccess) ce = cudaEventRecord(sl.ev_done, sl.stream);
-        if (ce != cudaSuccess) { rc = cuda_fail(ctx, ce, "level-2 D2H"); break; }
-        fl[cur].first = first; fl[cur].count = cnt; fl[cur].npair_lanes = nlanes; fl[cur].busy = true;
-        ++launches; h2d += sl.in_bytes; d2h += nlanes * sizeof(SlotResult);
-    }
-    for (int k = 0; k < 2; ++k) {
-        if (rc) { if (W->slots[k].stream) cudaStreamSynchronize(W->slots[k].stream); fl[k].busy = false; }
-        else rc = collect(k);
+        CUDA_TRY(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, nlanes * sizeof(SlotResult), cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(ctx, cudaEventRecord(sl.ev_done, sl.stream));
+        sl.busy = true; sl.first = first; sl.count = cnt;
+        launches += nl; h2d += sl.in_bytes; d2h += nlanes * sizeof(SlotResult);
+        return 0;
+    };
+    auto worker_main = [&](size_t k) {
+        Worker& W = *ctx->workers[k];
+        int r = 0;
+        if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
+        if (!r && !W.ready) {
+            for (Slot& sl : W.slots) if (!r) r = slot_init(ctx, sl);
+            W.ready = (r == 0);
+        }
+        int cur = 0;
+        while (!r && !first_err.load(std::memory_order_relaxed)) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            Slot& sl = W.slots[cur];
+            cur ^= 1;
+            const double t0 = now_ms();
+            if ((r = collect(sl))) break;
+            const size_t first = c * chunk;
+            const double t1 = now_ms();
+            r = submit(sl, first, std::min(chunk, elig.size() - first));
+            if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu chunk %zu collect %.2f submit %.2f ms\n", k, c, t1 - t0, now_ms() - t1);
+        }
+        const double t2 = now_ms();
+        for (Slot& sl : W.slots) {
+            if (r) { if (sl.stream) cudaStreamSynchronize(sl.stream); sl.busy = false; }
+            else r = collect(sl);
+        }
+        if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu drain %.2f ms\n", k, now_ms() - t2);
+        if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
+    };
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    if (nworkers == 1) worker_main(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < nworkers; ++k) th.emplace_back(worker_main, k);
+        worker_main(0);
+        for (auto& t : th) t.join();
     }
     cudaSetDevice(prev_dev);
     {
         std::lock_guard<std::mutex> g(ctx->err_mu);
-        ctx->stats.kernel_launches += launches; ctx->stats.h2d_bytes += h2d; ctx->stats.d2h_bytes += d2h;
+        ctx->stats.kernel_launches += launches.load(); ctx->stats.h2d_bytes += h2d.load(); ctx->stats.d2h_bytes += d2h.load();
+        ctx->stats.tasks += elig.size();
     }
-    return rc;
+    return first_err.load();
 }
 
 int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
