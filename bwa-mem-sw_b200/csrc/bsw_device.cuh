@@ -80,11 +80,15 @@ struct LaunchArgs {
     uint32_t         ntiles;
     int32_t          qmax;         // max qlen over the launch (sizes the per-lane row buffer)
     int32_t          nqw_max;      // max query words per lane over the launch (K1)
+    int32_t          wmax;         // max band over the launch (K2: decides whether the row buffer may be a ring)
     // K3 (fused seed task) only: tiles come in (left, right) pairs, seeds[pair*32 + lane]
     const SeedParam* seeds;
     int32_t          w, pen_clip5, pen_clip3;
 };
 
 constexpr int STATUS_OK = 0;
+constexpr int STATUS_OVERFLOW = 1;  // K1R: the live window outgrew the ring; the host reruns the task on K2
+constexpr int K1R_RING = 512;       // columns of K1R's row ring
+constexpr uint32_t TILE_ONEHOT = 0x8000u;   // TileHdr.nqw_ntw bit 15: the query block holds match planes (K0 builds them)
 
 }  // namespace bsw

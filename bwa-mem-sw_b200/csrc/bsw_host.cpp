@@ -94,6 +94,7 @@ struct bsw_ctx {
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 32768;
+    int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     bool kernel_timing = true;     // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms)
     std::mutex mu;                 // serialises batch calls on this context
@@ -242,11 +243,12 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
         a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out;
-        a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max;
+        a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
         cudaStream_t st = spread ? (nl % 3 == 0 ? s.stream : s.side[nl % 3 - 1]) : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
                       : (L.kind == 3) ? k1p_launch(a, sym, st)
-                                      : k2_launch(a, L.generic, st);
+                      : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
+                                      : k2_launch(a, L.generic, ctx->k2_warps, st);
         if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : (L.kind == 3 ? "K1P launch" : "K2 launch"));
         ++nl;
     }
@@ -330,7 +332,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
 }
 
 // Wait for the slot's chunk and scatter its results to out[first + task].
-int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st)
+int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow)
 {
     if (!s.busy) return 0;
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
@@ -347,6 +349,7 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
         const int64_t t = P.slot_task[k];
         if (t < 0) continue;
         const SlotResult& r = h_out[k];
+        if (r.status == STATUS_OVERFLOW) { overflow->push_back(first + (size_t)t); continue; }     // K1R ring too small: rerun on K2
         if (r.status != STATUS_OK) bad = 1;
         cell_sum += (uint32_t)r.cells;
         bsw_result& o = out[first + (size_t)t];
@@ -354,6 +357,7 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
         if (cells) cells[first + (size_t)t] = (uint32_t)r.cells;
     }
     st->tasks += s.count; st->cells += cell_sum; st->kernel_ms += ms;
+    (void)overflow;
     if (bad) { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
     return 0;
 }
@@ -373,16 +377,15 @@ Worker* get_worker(bsw_ctx* ctx, size_t k)
 // shared counter, alternating between their two stream slots.  Workers are bound round-robin to the devices, so a
 // multi-GPU context balances dynamically -- the GPU analogue of task_parse handing the next task to the first PE
 // with room (sw_pe_array_task_parse.v:1600-1650).  No collective: results land in out[task].
-int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out,
+                          uint32_t* cells, int force_kernel, std::vector<size_t>* overflow_out)
 {
-    if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
-    if (n == 0) return BSW_OK;
-    std::lock_guard<std::mutex> lock(ctx->mu);
     const double w0 = now_ms();
     DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
     int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
     if (rc) return rc;
     SchedOptions opt = ctx->opt;
+    if (force_kernel >= 0) opt.force_kernel = force_kernel;
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
@@ -398,10 +401,12 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
     std::atomic<int> first_err(0);
     std::mutex stat_mu;
     LocalStats total;
+    std::vector<size_t> overflow_all;
 
     auto worker_main = [&](size_t k) {
         Worker& W = *ctx->workers[k];
         LocalStats st;
+        std::vector<size_t> ovf;
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
         if (!r && !W.ready) {
@@ -419,7 +424,7 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
             Slot& s = W.slots[cur];
             cur ^= 1;
             const double c0 = T();
-            if ((r = slot_collect(ctx, s, out, cells, &st))) break;
+            if ((r = slot_collect(ctx, s, out, cells, &st, &ovf))) break;
             if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(c) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
             const size_t first = c * chunk, count = std::min(chunk, n - first);
             const double v0 = now_ms();
@@ -433,11 +438,12 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
         if (trace) tr += "w" + std::to_string(k) + " drain " + std::to_string(T());
         for (Slot& s : W.slots) {
             if (r) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }    // leave the device quiescent
-            else r = slot_collect(ctx, s, out, cells, &st);
+            else r = slot_collect(ctx, s, out, cells, &st, &ovf);
         }
         if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
         if (trace) { tr += " done " + std::to_string(T()) + "\n"; fputs(tr.c_str(), stderr); }
         std::lock_guard<std::mutex> g(stat_mu);
+        overflow_all.insert(overflow_all.end(), ovf.begin(), ovf.end());
         total.pack_ms += st.pack_ms; total.validate_ms += st.validate_ms; total.kernel_ms += st.kernel_ms;
         total.h2d += st.h2d; total.d2h += st.d2h; total.launches += st.launches; total.tasks += st.tasks; total.cells += st.cells;
     };
@@ -458,8 +464,37 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
         S.h2d_bytes += total.h2d; S.d2h_bytes += total.d2h; S.kernel_ms += total.kernel_ms;
         S.pack_ms += (total.pack_ms + total.validate_ms) / (double)nworkers;     // average per worker = wall share
         S.wall_ms += now_ms() - w0;
+        S.tasks -= overflow_all.size();          // counted again by the rerun
     }
+    if (overflow_out) overflow_out->swap(overflow_all);
     return first_err.load();
+}
+
+// Gathers a subset of a task source (the K1R overflow list).
+struct SubsetSrc { const TaskSource* base; const size_t* idx; };
+void fill_subset(const void* self, size_t first, size_t count, ExtTask* out)
+{
+    const SubsetSrc& S = *static_cast<const SubsetSrc*>(self);
+    for (size_t k = 0; k < count; ++k) S.base->fill(S.base->self, S.idx[first + k], 1, out + k);
+}
+
+int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+{
+    if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (n == 0) return BSW_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::vector<size_t> overflow;
+    int rc = run_extensions_locked(ctx, params, src, n, out, cells, -1, &overflow);
+    if (rc || overflow.empty()) return rc;
+    // K1R tasks whose live window outgrew the ring: rerun them on K2 (whole task, from scratch) and scatter
+    std::sort(overflow.begin(), overflow.end());
+    const SubsetSrc sub{ &src, overflow.data() };
+    std::vector<bsw_result> r2(overflow.size());
+    std::vector<uint32_t> c2(cells ? overflow.size() : 0);
+    rc = run_extensions_locked(ctx, params, TaskSource{ &sub, fill_subset }, overflow.size(), r2.data(), cells ? c2.data() : nullptr, 2, nullptr);
+    if (rc) return rc;
+    for (size_t k = 0; k < overflow.size(); ++k) { out[overflow[k]] = r2[k]; if (cells) cells[overflow[k]] = c2[k]; }
+    return BSW_OK;
 }
 
 // ---- task sources ----
@@ -585,6 +620,8 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "k2_warps") { if (value != 1 && value != 4) return BSW_EINVAL; ctx->k2_warps = (int)value; }
+    else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
@@ -1023,15 +1060,21 @@ int bsw_resident_fetch(bsw_ctx* ctx, bsw_resident* R, bsw_result* out, uint32_t*
     const Plan& P = s.plan;
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, P.slots.size() * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
+    size_t novf = 0;
     for (size_t k = 0; k < P.slots.size(); ++k) {
         const int64_t t = P.slot_task[k];
         if (t < 0) continue;
         const SlotResult& r = s.h_out[k];
+        if (r.status == STATUS_OVERFLOW) ++novf;
         bsw_result& o = out[(size_t)t];
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
         if (cells) cells[(size_t)t] = (uint32_t)r.cells;
     }
     cudaSetDevice(prev);
+    if (novf) {     // a resident batch is measurement-only and has no rerun stage
+        set_error(ctx, std::to_string(novf) + " tasks outgrew K1R's ring; use the batch call (it reruns them on K2) or set option ring=0");
+        return BSW_ERANGE;
+    }
     return BSW_OK;
 }
 

@@ -155,10 +155,16 @@ BSW_HD int k1_lookup(uint32_t nib, uint32_t rlo, uint32_t rhi)
 // One extension.  eh/qs point at this lane's column 0 / word 0 (stride K1_S); tg at this lane's target word 0 in the
 // tiled arena (stride K1_S).  eh must have qlen + 1 + K1_EH_SLACK columns; qs holds the tile's nqw_tile packed query
 // words of this lane and has room for nqw_max + K1_QS_EXTRA words.
-template <int VARIANT, int GENERIC, int SYM>
+// RING = 0: eh holds every column of the query.  RING = R (power of two): K1R, long tasks -- eh is a ring of R columns
+// indexed by (column & (R-1)); it only has to hold the live window [beg, end] of a row, which the narrowing keeps a few
+// hundred columns wide even for 10 kb reads.  A row whose candidate window does not fit ends the task with
+// STATUS_OVERFLOW (the host reruns it on K2).  In ring mode qs points at read-only global memory (match planes already
+// built by the K0 gather), so prep must be false.
+template <int VARIANT, int GENERIC, int SYM, int RING = 0>
 BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const int h0, const int w, const int nqw_tile,
                     uint32_t* eh, uint32_t* qs, const uint32_t* tg, SlotResult& res, const bool prep = true)
 {
+#define BSW_EHA(J) (eh + (RING ? ((J) & (RING - 1)) : (J)) * K1_S)
     constexpr bool ONEHOT = (VARIANT == 1 && GENERIC == 0);     // the branch-free path of the +a/-b scoring
     const int o_del = P.o_del, e_del = P.e_del, e_ins = P.e_ins;
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
@@ -211,7 +217,8 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     {
         eh[0] = (uint32_t)h0 << 16;
         int hv = h0 - P.o_ins;
-        for (int j = 1; j <= qlen; ++j) { hv -= e_ins; eh[j * K1_S] = (uint32_t)imax(hv, 0) << 16; }
+        const int jinit = RING ? imin(qlen, RING - 1) : qlen;
+        for (int j = 1; j <= jinit; ++j) { hv -= e_ins; eh[j * K1_S] = (uint32_t)imax(hv, 0) << 16; }
     }
 
     int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;   // sx:889,1009,919,1019,1029,929
@@ -240,21 +247,26 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             // rare: the band clamp moved the start past mj+2; a zero in between ends the row (end' <= beg)
             const int zend = imin(j0, lim);
             for (int z = stopmin; z < zend; ++z)
-                if ((eh[z * K1_S] >> 16) == 0) { lim = imin(lim, z); break; }
+                if ((*BSW_EHA(z) >> 16) == 0) { lim = imin(lim, z); break; }
+        }
+        if (RING && lim - j0 + 2 > RING) {                                       // the live window does not fit the ring
+            res.score = 0; res.qle = 0; res.tle = 0; res.gtle = 0; res.gscore = 0; res.max_off = 0; res.cells = 0;
+            res.status = STATUS_OVERFLOW;
+            return;
         }
         int fc;                                                                  // first column (sx:1796,1795,1880,1835,849)
         if (VARIANT == 1 || j0 == 0) fc = imax(h0 - (o_del + e_del * (i + 1)), 0); else fc = 0;
         if (VARIANT == 1) {
             // trim the zero prefix (beg' = last zero + 1, sx:1766-1769) and the zero suffix (end' = first zero
             // >= mj+2, sx:1779,1782-1789) of the candidate window; interior zeros are caught chunk by chunk.
-            while (j0 < lim && j0 <= resetmax && (eh[j0 * K1_S] >> 16) == 0) ++j0;
-            while (lim > j0 && lim - 1 >= stopmin && (eh[(lim - 1) * K1_S] >> 16) == 0) --lim;
+            while (j0 < lim && j0 <= resetmax && (*BSW_EHA(j0) >> 16) == 0) ++j0;
+            while (lim > j0 && lim - 1 >= stopmin && (*BSW_EHA(lim - 1) >> 16) == 0) --lim;
         }
         uint32_t h1 = (uint32_t)fc << 16, f = 0;                                 // packed {value, 0}
         int b_eff = j0;
         int mkey = K1_KEY_NONE;
         int j = j0;
-        uint32_t* ehp = eh + j * K1_S;
+        uint32_t* ehp = BSW_EHA(j);
 
         // One DP cell on the branch-free path (see the header comment).  X = match bits (ONEHOT) or query nibbles (GENERIC).
 #define BSW_K1_FAST(K, W, X, LIVE)                                                                   \
@@ -282,7 +294,8 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                 const int qi = j >> 3;
                 x = funnel_r(qs[qi * K1_S], qs[(qi + 1) * K1_S], (j & 7) * 4);
             }
-            if (VARIANT == 1) {
+            if (RING) ehp = BSW_EHA(j);
+            if (VARIANT == 1 && (!RING || (j & (RING - 1)) <= RING - 8)) {      // ring: a chunk that wraps goes cell by cell
                 const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
                 const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
                 int ckey = K1_KEY_NONE;                      // chunk-local key: (h << 16) + k
@@ -327,6 +340,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             // careful path: cell by cell, with the narrowing events (V1) or the V2 recurrence
             const int kmax = nv < 8 ? nv : 8;
             for (int k = 0; k < kmax; ++k, ++j, ehp += K1_S) {
+                if (RING) ehp = BSW_EHA(j);
                 const uint32_t wd = *ehp;
                 int M = (int)(wd >> 16), e = (int)(wd & 0xffffu);
                 if (VARIANT == 1 && M == 0) {
@@ -357,7 +371,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
         const int e_eff = lim;
         const int h1v = (int)(h1 >> 16);
         if (e_eff > b_eff) cells += (uint32_t)(e_eff - b_eff);
-        eh[e_eff * K1_S] = h1;                                                   // eh[end] = {h1, e=0}: sx:1775,1904
+        *BSW_EHA(e_eff) = h1;                                                    // eh[end] = {h1, e=0}: sx:1775,1904
         if (VARIANT == 2) { if (h1v != 0) lnz = e_eff; }
         const int j_after = e_eff > b_eff ? e_eff : b_eff;                       // value of j after the reference's loop
         if (j_after == qlen) {                                                   // sx:1768,1913
@@ -386,6 +400,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     }
     res.score = max; res.qle = max_j + 1; res.tle = max_i + 1; res.gtle = max_ie + 1;     // sx:1315-1375,1841,1868,1794
     res.gscore = gscore; res.max_off = max_off; res.cells = (int32_t)cells; res.status = STATUS_OK;   // sx:1792,1815
+#undef BSW_EHA
 }
 
 }  // namespace bsw

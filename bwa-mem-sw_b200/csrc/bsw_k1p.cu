@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(K1P_NT) k1p_extend_kernel(const __grid_constan
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TileHdr ha = A.tiles[2 * blockIdx.x], hb = A.tiles[2 * blockIdx.x + 1];
-    const uint32_t nqa = ha.nqw_ntw & 0xffffu, nqb = hb.nqw_ntw & 0xffffu;
+    const uint32_t nqa = ha.nqw_ntw & 0x7fffu, nqb = hb.nqw_ntw & 0x7fffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     const size_t qwords = (size_t)(A.nqw_max + K1_QS_EXTRA) * K1P_NT;
     uint32_t* qsa = reinterpret_cast<uint32_t*>(smem_raw + K1P_HDR_BYTES);

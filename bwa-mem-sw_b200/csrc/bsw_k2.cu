@@ -1,4 +1,4 @@
-// bsw_k2.cu -- K2: intra-task extension kernel for long tasks, one 4-warp CTA per task (sm_100a).
+// bsw_k2.cu -- K2: intra-task extension kernel for long tasks, one CTA of NW = 1 or 4 warps per task (sm_100a).
 //
 // The reference caps a task at qlen <= 255 / 2048 bases (query_mem 2048x4b, eh_arr 256 entries:
 // sw_pe_array_proc_element.v:347-350, sw_pe_array_sw_extend.v:512-515); BASELINE config 4 asks for
@@ -27,8 +27,8 @@
 
 namespace bsw {
 
-constexpr int K2_WARPS = 4;
-constexpr int K2_NT = 32 * K2_WARPS;
+constexpr int K2_MAXW = 4;               // warps per task: template parameter NW in {1, 4}
+constexpr int K2_RING = 2048;            // row-buffer columns kept in shared memory (a ring once the query is longer)
 constexpr int K2_GROUP = 256;           // columns per warp step
 constexpr int K2_HDR_BYTES = 128;       // mbarrier (8 B) + cross-warp exchange words
 
@@ -51,16 +51,22 @@ __device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
     return (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
 }
 
-template <int GENERIC>
-__global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
+template <int GENERIC, int K2_WARPS>
+__global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
 {
+    constexpr int K2_NT = 32 * K2_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileHdr hd = A.tiles[blockIdx.x];
     const uint32_t slot = hd.slot0;
     const SlotParam sp = A.slots[slot];
     const int qlen = sp.qlen, tlen = sp.tlen, h0 = sp.h0, w = sp.w;
-    const int qcap = (A.qmax + 1 + K2_GROUP - 1) & ~(K2_GROUP - 1);      // row buffer columns, multiple of 256
+    const int qcap = (A.qmax + 1 + K2_GROUP - 1) & ~(K2_GROUP - 1);      // query columns, multiple of 256
+    // The row buffer only has to hold the live window [beg & ~255, end] of a row (at most 2w+1+255 columns), so for long
+    // queries it is a ring of K2_RING columns indexed by (column & rm); groups are 256-aligned, so a group never wraps.
+    const bool ring = qcap > K2_RING && 2 * A.wmax + 1 + 2 * K2_GROUP <= K2_RING;
+    const int rcap = ring ? K2_RING : qcap;
+    const int rm = ring ? (K2_RING - 1) : 0x7fffffff;
     const int nqw = (qlen + 7) >> 3;
     const uint32_t qbytes = (uint32_t)((nqw * 4 + 15) & ~15);
 
@@ -69,8 +75,8 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
     int* xhl  = xagg + K2_WARPS;                                                  // [K2_WARPS] h of the group's last column
     int* xkey = xhl + K2_WARPS;                                                   // [K2_WARPS] per-warp arg-max key
     uint32_t* qs = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);          // qcap/8 words (+ pad)
-    uint32_t* zb = qs + (qcap >> 3) + 4;                                          // qcap/32 words of zero bits
-    uint32_t* eh = zb + (qcap >> 5) + 4;                                          // qcap + 8 words
+    uint32_t* zb = qs + (qcap >> 3) + 4;                                          // rcap/32 words of zero bits
+    uint32_t* eh = zb + (rcap >> 5) + 4;                                          // rcap + 8 words
     eh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(eh) + 15) & ~(uintptr_t)15);
 
     if (tid == 0) {
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
     const int e8 = 8 * e_ins, e256 = K2_GROUP * e_ins;
 
     // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
-    for (int j = tid; j < qcap + 8; j += K2_NT) {
+    for (int j = tid; j < rcap + 8; j += K2_NT) {
         int hv = (j == 0) ? h0 : imax(h0 - A.p.o_ins - j * e_ins, 0);
         if (j > qlen) hv = 0;
         eh[j] = (uint32_t)hv;
@@ -143,8 +149,8 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
             int hh[8], fl[8];
             int run = 0, fin0 = 0;
             if (active) {
-                const uint4 wa = *reinterpret_cast<const uint4*>(eh + jl);
-                const uint4 wb = *reinterpret_cast<const uint4*>(eh + jl + 4);
+                const uint4 wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
+                const uint4 wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
                 wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
                 const uint32_t qw = qs[jl >> 3];
                 const uint32_t x = GENERIC ? qw : (qw ^ trep);
@@ -215,19 +221,19 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
                     oa.x = enew[0] | (uint32_t)((lo == 0) ? fc : hleft);
                     oa.y = enew[1] | (uint32_t)h[0]; oa.z = enew[2] | (uint32_t)h[1]; oa.w = enew[3] | (uint32_t)h[2];
                     ob.x = enew[4] | (uint32_t)h[3]; ob.y = enew[5] | (uint32_t)h[4]; ob.z = enew[6] | (uint32_t)h[5]; ob.w = enew[7] | (uint32_t)h[6];
-                    *reinterpret_cast<uint4*>(eh + jl) = oa;
-                    *reinterpret_cast<uint4*>(eh + jl + 4) = ob;
+                    *reinterpret_cast<uint4*>(eh + (jl & rm)) = oa;
+                    *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = ob;
                 } else {
                     // boundary lane: store cells [lo,hi) and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         if (k >= lo && k <= hi) {
                             const int h1 = (k == lo) ? fc : (k ? h[k - 1] : hleft);
-                            eh[jl + k] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
+                            eh[(jl + k) & rm] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
                         }
                     }
                 }
-                reinterpret_cast<unsigned char*>(zb)[jl >> 3] = (unsigned char)zbits;
+                reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
             }
             hcarry = xhl[K2_WARPS - 1];          // only consumed when another round follows (then the last warp was active)
         }
@@ -236,10 +242,12 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
         __syncthreads();                                                   // (3) row buffer, zero bits and keys visible
 
         // ---- row epilogue (identical in every thread of the CTA) ----
-        key = imax(imax(xkey[0], xkey[1]), imax(xkey[2], xkey[3]));
+        key = xkey[0];
+#pragma unroll
+        for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
         const int m = key >> 16, mj = key & 0xffff;
         cells += (unsigned long long)(lim - j0);
-        const int h1 = (int)(eh[lim] & 0xffffu);
+        const int h1 = (int)(eh[lim & rm] & 0xffffu);
         if (lim == qlen) {                                                         // sx:1768,1913
             if (!(gscore > h1)) { max_ie = i; gscore = h1; }                       // sx:1941,1829,1831
         }
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
         int cb = -1, ce = 0x7fffffff;
         for (int wbase = (j0 >> 5); wbase <= ((lim - 1) >> 5); wbase += 32) {
             const int wi = wbase + lane;
-            const uint32_t zw = (wi <= ((lim - 1) >> 5)) ? zb[wi] : 0u;
+            const uint32_t zw = (wi <= ((lim - 1) >> 5)) ? zb[wi & (rm >> 5)] : 0u;
             const uint32_t za = zw & k2_range_mask(wi * 32, j0, mj - 1);
             const uint32_t ze = zw & k2_range_mask(wi * 32, mj + 1, lim - 1);
             if (za) cb = imax(cb, wi * 32 + 31 - __clz(za));
@@ -280,30 +288,33 @@ __global__ void __launch_bounds__(K2_NT) k2_extend_kernel(const __grid_constant_
     }
 }
 
-size_t k2_smem_bytes(int qmax)
+size_t k2_smem_bytes(int qmax, int wmax)
 {
     const size_t qcap = ((size_t)qmax + 1 + K2_GROUP - 1) & ~(size_t)(K2_GROUP - 1);
-    return (size_t)K2_HDR_BYTES + ((qcap >> 3) + 4 + (qcap >> 5) + 4 + qcap + 8) * 4u + 16u;
+    const bool ring = qcap > (size_t)K2_RING && 2 * (size_t)wmax + 1 + 2 * K2_GROUP <= (size_t)K2_RING;
+    const size_t rcap = ring ? (size_t)K2_RING : qcap;
+    return (size_t)K2_HDR_BYTES + ((qcap >> 3) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
 }
 
-template <int GENERIC>
+template <int GENERIC, int NW>
 static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
 {
     if (!a.ntiles) return cudaSuccess;
-    const size_t smem = k2_smem_bytes(a.qmax);
-    auto kern = k2_extend_kernel<GENERIC>;
+    const size_t smem = k2_smem_bytes(a.qmax, a.wmax);
+    auto kern = k2_extend_kernel<GENERIC, NW>;
     // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
     // value would race with another thread's launch of the same kernel
     if (smem > 232448) return cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (err != cudaSuccess) return err;
-    kern<<<a.ntiles, K2_NT, smem, st>>>(a);
+    kern<<<a.ntiles, 32 * NW, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st)
+cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, cudaStream_t st)
 {
-    return generic ? k2_launch_t<1>(a, st) : k2_launch_t<0>(a, st);
+    if (warps >= K2_MAXW) return generic ? k2_launch_t<1, 4>(a, st) : k2_launch_t<0, 4>(a, st);
+    return generic ? k2_launch_t<1, 1>(a, st) : k2_launch_t<0, 1>(a, st);
 }
 
 }  // namespace bsw

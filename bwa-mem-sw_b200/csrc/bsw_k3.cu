@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(K3_NT) k3_seed_kernel(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const TileHdr hl = A.tiles[2 * blockIdx.x], hr = A.tiles[2 * blockIdx.x + 1];
-    const uint32_t nql = hl.nqw_ntw & 0xffffu, nqr = hr.nqw_ntw & 0xffffu;
+    const uint32_t nql = hl.nqw_ntw & 0x7fffu, nqr = hr.nqw_ntw & 0x7fffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     const size_t qwords = (size_t)(A.nqw_max + K1_QS_EXTRA) * K3_NT;
     uint32_t* qsl = reinterpret_cast<uint32_t*>(smem_raw + K3_HDR_BYTES);

@@ -13,6 +13,9 @@ cudaError_t k0_launch(const GatherArgs& a, cudaStream_t st);
 cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
 size_t k1_smem_bytes(int qmax, int nqw_max);
 
+// K1R: K1's lane function over a 512-column ring for long tasks (V1); overflowing tasks come back with STATUS_OVERFLOW.
+cudaError_t k1r_launch(const LaunchArgs& a, int generic, int sym, cudaStream_t st);
+
 // K1P: two tasks per lane, int16x2-packed scores (V1 recurrence, match/mismatch scoring).  a.tiles = (A, B) tile pairs.
 cudaError_t k1p_launch(const LaunchArgs& a, int sym, cudaStream_t st);
 size_t k1p_smem_bytes(int qmax, int nqw_max);
@@ -23,8 +26,8 @@ cudaError_t k3_launch(const LaunchArgs& a, int variant, int generic, int sym, cu
 size_t k3_smem_bytes(int qmax, int nqw_max);
 
 // K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  Variant 1 only.
-cudaError_t k2_launch(const LaunchArgs& a, int generic, cudaStream_t st);
-size_t k2_smem_bytes(int qmax);
+cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, cudaStream_t st);
+size_t k2_smem_bytes(int qmax, int wmax);
 
 // INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
 // streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.

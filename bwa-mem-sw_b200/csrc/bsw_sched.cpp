@@ -133,6 +133,8 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
                 if (!e && (t.qlen > k1cap || opt.force_kernel == 2)) e = BSW_ERANGE;
             }
             if (longtask) c |= 2;
+            // K1R needs the first row (min(qlen, w+1) columns + end slot) inside the ring
+            if (longtask && opt.ring && opt.variant == 1 && opt.force_kernel != 2 && std::min(t.qlen, t.w + 1) + 2 <= K1R_RING) c |= 4;
         }
         cls[i] = c;
         if (e) {
@@ -158,10 +160,12 @@ static inline size_t k1p_tile_smem(int qmax, int nqw)
 {
     return 128 + (size_t)2 * (size_t)(nqw + 8) * TILE_LANES * 4u + (size_t)(qmax + 1 + K1_EH_SLACK) * TILE_LANES * 8u;
 }
-static inline size_t k2_task_smem(int qmax)
+static inline size_t k2_task_smem(int qmax, int wmax)
 {
     const size_t qcap = ((size_t)qmax + 1 + 255) & ~(size_t)255;
-    return 128 + ((qcap >> 3) + 4 + (qcap >> 5) + 4 + qcap + 8) * 4u + 16u;
+    const bool ring = qcap > 2048 && 2 * (size_t)wmax + 513 <= 2048;
+    const size_t rcap = ring ? 2048 : qcap;
+    return 128 + ((qcap >> 3) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
 }
 static inline int occupancy(size_t smem)
 {
@@ -179,17 +183,18 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
     if (n == 0) return;
 
-    // sort key (32 bit, descending cost first): [class:2][qlen:14][tlen/4:10][h0/2:6]; the order is only a
+    // sort key (32 bit, descending cost first): [class:3][qlen:13][tlen/4:10][h0/2:6]; the order is only a
     // scheduling heuristic (any order gives the same results), so long lengths may saturate their field.
+    // classes: 0 K1 fast, 1 K1 matrix, 2 K1R fast, 3 K1R matrix, 4 K2 fast, 5 K2 matrix
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
     key.resize(n); order.resize(n); tmp.resize(n); hist.assign(65537, 0);
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& t = tasks[i];
-        const uint32_t c = ((cls[i] & 2u) ? 2u : 0u) | (cls[i] & 1u);
-        const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 2, 16383) : (uint32_t)std::min(t.qlen, 16383);
+        const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
+        const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 3, 8191) : (uint32_t)std::min(t.qlen, 8191);
         const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
-        key[i] = (c << 30) | ((16383u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
+        key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
     }
     // LSD radix, two 16-bit digits
     for (size_t i = 0; i < n; ++i) ++hist[(key[i] & 0xffffu) + 1];
@@ -210,20 +215,21 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     };
     size_t i = 0;
     while (i < n) {
-        const uint32_t c = key[order[i]] >> 30;
+        const uint32_t c = key[order[i]] >> 29;
         size_t cend = i;
-        while (cend < n && (key[order[cend]] >> 30) == c) ++cend;
-        const bool is_k2 = (c & 2u) != 0;
-        const bool is_pair = !is_k2 && (c & 1u) == 0 && opt.pair && opt.variant == 1;
+        while (cend < n && (key[order[cend]] >> 29) == c) ++cend;
+        const bool is_k2 = c >= 4u;
+        const bool is_ring = (c & 6u) == 2u;
+        const bool is_pair = c == 0u && opt.pair && opt.variant == 1;
         Launch L{};
-        L.kind = is_k2 ? 2 : (is_pair ? 3 : 1); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
+        L.kind = is_k2 ? 2 : (is_ring ? 4 : (is_pair ? 3 : 1)); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
         int occ0 = 0;
         while (i < cend) {
             // one K2 task, one K1 tile of 32 tasks, or one K1P pair of tiles (64 tasks: lane l = tasks 2l and 2l+1)
             const size_t ntask = is_k2 ? 1 : std::min<size_t>(is_pair ? 2 * TILE_LANES : TILE_LANES, cend - i);
             const int nsub = is_pair ? 2 : 1;
             TileHdr hd[2];
-            int qmax = 0, nqw_max = 0;
+            int qmax = 0, nqw_max = 0, wmax = 0;
             for (int sub = 0; sub < nsub; ++sub) {
                 hd[sub] = TileHdr{};
                 hd[sub].slot0 = (uint32_t)plan->slots.size();
@@ -234,7 +240,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                     if (k < ntask) {
                         const uint32_t ti = order[i + k];
                         const ExtTask& t = tasks[ti];
-                        tq = std::max(tq, t.qlen); tt = std::max(tt, t.tlen);
+                        tq = std::max(tq, t.qlen); tt = std::max(tt, t.tlen); wmax = std::max(wmax, t.w);
                         plan->slots.push_back(SlotParam{ t.qlen, t.tlen, t.h0, t.w });
                         plan->slot_src.push_back(src[ti]);
                         plan->slot_task.push_back((int64_t)ti);
@@ -246,7 +252,10 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                         plan->slot_task.push_back(-1);
                     }
                 }
-                const int nqw = (tq + 7) >> 3, ntw = (tt + 7) >> 3;
+                int nqw = (tq + 7) >> 3;
+                const int ntw = (tt + 7) >> 3;
+                const bool planes = is_ring && (c & 1u) == 0;                   // K1R fast: K0 writes match planes
+                if (planes) nqw = 4 * (((tq + 31) >> 5) + 1);
                 if (is_k2) {
                     hd[sub].qoff16 = src[order[i]].qoff16;                      // K2 reads the source arena directly
                     hd[sub].toff16 = src[order[i]].toff16;
@@ -255,17 +264,18 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                     hd[sub].toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
                     ++plan->n_k1_tiles;
                 }
-                hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+                hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16) | (planes ? TILE_ONEHOT : 0u);
                 qmax = std::max(qmax, tq); nqw_max = std::max(nqw_max, nqw);
             }
-            const size_t smem = is_k2 ? k2_task_smem(qmax) : (is_pair ? k1p_tile_smem(qmax, nqw_max) : k1_tile_smem(qmax, nqw_max));
+            const size_t smem = is_ring ? (size_t)K1R_RING * TILE_LANES * 4u : is_k2 ? k2_task_smem(qmax, wmax) : (is_pair ? k1p_tile_smem(qmax, nqw_max) : k1_tile_smem(qmax, nqw_max));
             // bucket boundary: start a new launch when this tile would fit at >= 1.3x the occupancy of the launch
             const int occ = occupancy(smem);
+            L.wmax = std::max(L.wmax, wmax);
             if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw_max; }
             else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw_max); }   // saturated sort key (very long tasks)
-            else if (!is_k2 && occ * 10 >= occ0 * 13) {      // K2: one launch per class (measured: bucket tails cost more than occupancy gains)
+            else if (!is_k2 && !is_ring && occ * 10 >= occ0 * 13) {      // K2 / K1R: one launch per class (measured: bucket tails cost more than occupancy gains)
                 close_launch(L, (uint32_t)plan->tiles.size());
-                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; occ0 = occ;
+                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; L.wmax = wmax; occ0 = occ;
             }
             for (int sub = 0; sub < nsub; ++sub) plan->tiles.push_back(hd[sub]);
             i += ntask;

@@ -31,6 +31,8 @@ struct SchedOptions {
     int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
     int host_threads = 0;       // 0 = hardware concurrency (capped)
     bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
+    bool ring = false;          // long V1 tasks whose first row fits run on K1R (ring row buffer in K1's lane function).
+                                // Off by default: measured slower than K2 (3 warps/SM with a 512-column ring), see DESIGN.md
     bool pair = false;          // V1 + FAST tasks run two per lane (K1P, packed int16x2).  Off by default: measured slower
                                 // than K1 on B200 (occupancy halves with the doubled row buffer), see DESIGN.md section 5
 };
@@ -40,10 +42,11 @@ constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
 constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
 
 struct Launch {
-    int kind;          // 1 = K1, 2 = K2, 3 = K1P (tiles come in pairs: A tile, B tile), 5 = K3 (pairs: left tile, right tile)
+    int kind;          // 1 = K1, 2 = K2, 4 = K1R (long tasks, ring row buffer), 3 = K1P (tiles come in pairs: A tile, B tile), 5 = K3 (pairs: left tile, right tile)
     int generic;       // 1 = matrix lookup scoring
     uint32_t tile0, ntiles;
     int qmax, nqw_max;
+    int wmax;          // max band of the launch's tasks
 };
 
 struct Plan {
@@ -65,7 +68,7 @@ struct Plan {
 size_t source_arena_bound(const ExtTask* tasks, size_t n);
 
 // Fused validate + classify + pack (single pass, single thread).  cls: bit0 = needs matrix-lookup scoring (contains N,
-// or the matrix is not +a/-b), bit1 = long task (K2).  src[i] = offsets of task i's packed sequences in `arena`.
+// or the matrix is not +a/-b), bit1 = long task (K2 or K1R), bit2 = long task that may start on K1R.  src[i] = offsets of task i's packed sequences in `arena`.
 // Returns 0 or a negative BSW_E* code; on error *bad_task is the first offending task and msg explains.
 int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);

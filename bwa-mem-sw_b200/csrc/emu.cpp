@@ -26,7 +26,7 @@ template <int VARIANT, int GENERIC, int SYM>
 void run_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, const uint32_t* arena, SlotResult* out,
               int qmax, int nqw_max)
 {
-    const int nqw = (int)(hd.nqw_ntw & 0xffffu);
+    const int nqw = (int)(hd.nqw_ntw & 0x7fffu);
     std::vector<uint32_t> qs((size_t)(nqw_max + K1_QS_EXTRA) * K1_S, 0xdeadbeefu);
     std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1_S, 0xdeadbeefu);
     memcpy(qs.data(), arena + (size_t)hd.qoff16 * 4, (size_t)nqw * K1_S * 4);       // the TMA bulk copy
@@ -39,11 +39,25 @@ void run_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, co
     }
 }
 
+template <int GENERIC, int SYM>
+void run_ring_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, uint32_t* arena, SlotResult* out)
+{
+    const int nqw = (int)(hd.nqw_ntw & 0x7fffu);
+    std::vector<uint32_t> eh((size_t)K1R_RING * K1_S, 0xdeadbeefu);
+    for (int lane = 0; lane < K1_S; ++lane) {
+        const SlotParam& sp = slots[hd.slot0 + lane];
+        if (sp.qlen <= 0) continue;
+        k1_task<1, GENERIC, SYM, K1R_RING>(dp, sp.qlen, sp.tlen, sp.h0, sp.w, nqw, eh.data() + lane,
+                                           arena + (size_t)hd.qoff16 * 4 + lane, arena + (size_t)hd.toff16 * 4 + lane,
+                                           out[hd.slot0 + lane], false);
+    }
+}
+
 template <int SYM>
 void run_pair(const DevParams& dp, const TileHdr& ha, const TileHdr& hb, const SlotParam* slots, const uint32_t* arena,
               SlotResult* out, int qmax, int nqw_max)
 {
-    const int nqa = (int)(ha.nqw_ntw & 0xffffu), nqb = (int)(hb.nqw_ntw & 0xffffu);
+    const int nqa = (int)(ha.nqw_ntw & 0x7fffu), nqb = (int)(hb.nqw_ntw & 0x7fffu);
     const size_t qwords = (size_t)(nqw_max + K1_QS_EXTRA) * K1_S;
     std::vector<uint32_t> qsa(qwords, 0xdeadbeefu), qsb(qwords, 0xdeadbeefu);
     std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1P_CS, 0xdeadbeefu);
@@ -67,11 +81,22 @@ void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
 {
     for (uint32_t t = 0; t < P.n_k1_tiles; ++t) {
         const TileHdr& hd = P.tiles[t];
-        const int nqw = (int)(hd.nqw_ntw & 0xffffu), ntw = (int)(hd.nqw_ntw >> 16);
+        const int nqw = (int)(hd.nqw_ntw & 0x7fffu), ntw = (int)(hd.nqw_ntw >> 16);
         for (int lane = 0; lane < TILE_LANES; ++lane) {
             const SlotParam& sp = P.slots[hd.slot0 + lane];
             const SlotSrc& ss = P.slot_src[hd.slot0 + lane];
             const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0, own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
+            if (hd.nqw_ntw & TILE_ONEHOT) {
+                for (int m = 0; m * 4 < nqw; ++m) {
+                    uint32_t v[4];
+                    for (int u = 0; u < 4; ++u) v[u] = (4 * m + u < own_q) ? src[(size_t)ss.qoff16 * 4 + 4 * m + u] : 0u;
+                    for (uint32_t b = 0; b < 4; ++b) {
+                        uint32_t pl = k1_eq8(v[0], b) | (k1_eq8(v[1], b) << 8) | (k1_eq8(v[2], b) << 16) | (k1_eq8(v[3], b) << 24);
+                        if (32 * m >= sp.qlen) pl = 0;
+                        dst[(size_t)hd.qoff16 * 4 + (size_t)(4 * m + (int)b) * TILE_LANES + lane] = pl;
+                    }
+                }
+            } else
             for (int k = 0; k < nqw; ++k) dst[(size_t)hd.qoff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_q ? src[(size_t)ss.qoff16 * 4 + k] : 0u;
             for (int k = 0; k < ntw; ++k) dst[(size_t)hd.toff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_t ? src[(size_t)ss.toff16 * 4 + k] : 0u;
         }
@@ -83,7 +108,9 @@ void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
 extern "C" {
 
 // info[0] = launches, info[1] = tiles, info[2] = arena words, info[3] = padded lanes
-int bsw_emu_pair = 0;      // tests flip this to exercise K1 (one task per lane) and K1P (two per lane)
+int bsw_emu_pair = 0;
+int bsw_emu_force_kernel = 1;   // 1: everything on K1; 0: auto (long tasks -> K1R; tasks that need K2 make the call fail)
+int bsw_emu_k2_min_qlen = 384;      // tests flip this to exercise K1 (one task per lane) and K1P (two per lane)
 
 int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8_t* qbuf, const int64_t* qoff,
                               const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
@@ -109,7 +136,8 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
     const int sym = (params->o_del == params->o_ins && params->e_del == params->e_ins) ? 1 : 0;
 
     SchedOptions opt;
-    opt.variant = variant; opt.force_kernel = 1; opt.fast_matrix = fast; opt.host_threads = 4; opt.pair = bsw_emu_pair != 0;
+    opt.variant = variant; opt.force_kernel = bsw_emu_force_kernel; opt.fast_matrix = fast; opt.host_threads = 4; opt.pair = bsw_emu_pair != 0;
+    opt.k2_min_qlen = bsw_emu_k2_min_qlen;
     std::vector<ExtTask> v(n);
     for (size_t i = 0; i < n; ++i) {
         ExtTask& x = v[i];
@@ -138,6 +166,13 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
             }
             continue;
         }
+        if (L.kind == 4) {
+            for (uint32_t t = L.tile0; t < L.tile0 + L.ntiles; ++t) {
+                if (L.generic) { if (sym) run_ring_tile<1, 1>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); else run_ring_tile<1, 0>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); }
+                else           { if (sym) run_ring_tile<0, 1>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); else run_ring_tile<0, 0>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); }
+            }
+            continue;
+        }
         if (L.kind != 1) return BSW_ERANGE;
         for (uint32_t t = L.tile0; t < L.tile0 + L.ntiles; ++t) {
             const TileHdr& hd = P.tiles[t];
@@ -152,6 +187,7 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
         const int64_t t = P.slot_task[k];
         if (t < 0) { ++pad; continue; }
         const SlotResult& r = res[k];
+        if (r.status == STATUS_OVERFLOW) { if (cells) cells[t] = 0xffffffffu; bsw_result& z = out[t]; z.score = z.qle = z.tle = z.gtle = z.gscore = z.max_off = -999; continue; }
         bsw_result& o = out[t];
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
         if (cells) cells[t] = (uint32_t)r.cells;
@@ -218,7 +254,7 @@ template <int VARIANT, int GENERIC, int SYM>
 void run_seed_pair(const DevParams& dp, int w, int pc5, int pc3, const TileHdr& hl, const TileHdr& hr, const SlotParam* slots,
                    const SeedParam* seeds, const uint32_t* arena, SeedRecord* out, int qmax, int nqw_max)
 {
-    const int nql = (int)(hl.nqw_ntw & 0xffffu), nqr = (int)(hr.nqw_ntw & 0xffffu);
+    const int nql = (int)(hl.nqw_ntw & 0x7fffu), nqr = (int)(hr.nqw_ntw & 0x7fffu);
     const size_t qwords = (size_t)(nqw_max + K1_QS_EXTRA) * K1_S;
     std::vector<uint32_t> qsl(qwords, 0xdeadbeefu), qsr(qwords, 0xdeadbeefu);
     std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1_S, 0xdeadbeefu);

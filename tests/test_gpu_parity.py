@@ -270,3 +270,31 @@ def test_level2_host_orchestrated_and_long_flanks(B, O, ctx):
     finally:
         ctx.set_option("fused_l2", 1)
     assert_same(want, got2, "host-orchestrated")
+
+
+def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
+    """Option ring=1: long tasks run on K1R (ring row buffer); a task whose window outgrows the ring is rerun on K2."""
+    ctx.set_option("ring", 1)
+    try:
+        _k1r_cases(B, O, ctx)
+    finally:
+        ctx.set_option("ring", 0)
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=82))          # default: K2 (one warp per task, ring row buffer)
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=83), opts={"k2_warps": 4})
+    ctx.set_option("k2_warps", 1)
+
+
+def _k1r_cases(B, O, ctx):
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 20_000, seed=80), opts={"k2_min_qlen": 64})       # K1 + K1R mix
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=81, n_frac=0.02), opts={"k2_min_qlen": 64}, o_del=4, e_del=2, o_ins=7, e_ins=1)
+    rng = np.random.default_rng(5)
+    qs, ts, h0, w = [], [], [], []
+    for k in range(40):                                       # near-perfect 3 kb matches with a big h0: windows grow past 510 columns
+        q = rng.integers(0, 4, 3000).astype(np.uint8)
+        t = np.concatenate([q, q[:200]]).astype(np.uint8)
+        t[rng.random(len(t)) < 0.01] = 0
+        qs.append(q); ts.append(t); h0.append(400 if k % 2 == 0 else 30); w.append(400)
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
+    both(B, O, ctx, t)
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=84))
