@@ -110,7 +110,8 @@ extern "C" {
 // info[0] = launches, info[1] = tiles, info[2] = arena words, info[3] = padded lanes
 int bsw_emu_pair = 0;
 int bsw_emu_force_kernel = 1;   // 1: everything on K1; 0: auto (long tasks -> K1R; tasks that need K2 make the call fail)
-int bsw_emu_k2_min_qlen = 384;      // tests flip this to exercise K1 (one task per lane) and K1P (two per lane)
+int bsw_emu_k2_min_qlen = 384;
+int bsw_emu_ring = 0;           // 1: long tasks go to K1R (the ring-buffer lane function)      // tests flip this to exercise K1 (one task per lane) and K1P (two per lane)
 
 int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8_t* qbuf, const int64_t* qoff,
                               const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
@@ -137,7 +138,7 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
 
     SchedOptions opt;
     opt.variant = variant; opt.force_kernel = bsw_emu_force_kernel; opt.fast_matrix = fast; opt.host_threads = 4; opt.pair = bsw_emu_pair != 0;
-    opt.k2_min_qlen = bsw_emu_k2_min_qlen;
+    opt.k2_min_qlen = bsw_emu_k2_min_qlen; opt.ring = bsw_emu_ring != 0;
     std::vector<ExtTask> v(n);
     for (size_t i = 0; i < n; ++i) {
         ExtTask& x = v[i];
