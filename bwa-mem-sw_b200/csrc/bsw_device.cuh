@@ -81,6 +81,7 @@ struct LaunchArgs {
     int32_t          qmax;         // max qlen over the launch (sizes the per-lane row buffer)
     int32_t          nqw_max;      // max query words per lane over the launch (K1)
     int32_t          wmax;         // max band over the launch (K2: decides whether the row buffer may be a ring)
+    int32_t          ring_cols;    // K2S: columns of the per-task row ring (power of two)
     // K3 (fused seed task) only: tiles come in (left, right) pairs, seeds[pair*32 + lane]
     const SeedParam* seeds;
     int32_t          w, pen_clip5, pen_clip3;

@@ -229,7 +229,7 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
 // Host statistics accumulated by one worker and merged once per call.
 struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0; };
 
-int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch)
+int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, bool k2_sub = true)
 {
     const Plan& P = s.plan;
     size_t nl = 0;
@@ -248,6 +248,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
                       : (L.kind == 3) ? k1p_launch(a, sym, st)
                       : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
+                      : (L.kind == 2 && k2_sub && (a.ring_cols = k2s_ring_cols(L.qmax, L.wmax)) > 0) ? k2s_launch(a, L.generic, st)
                                       : k2_launch(a, L.generic, ctx->k2_warps, st);
         if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : (L.kind == 3 ? "K1P launch" : "K2 launch"));
         ++nl;
@@ -316,7 +317,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if ((rc = enqueue_gather(ctx, s))) return rc;
-    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub))) return rc;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, nslots * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
@@ -385,7 +386,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
     if (rc) return rc;
     SchedOptions opt = ctx->opt;
-    if (force_kernel >= 0) opt.force_kernel = force_kernel;
+    if (force_kernel >= 0) { opt.force_kernel = force_kernel; opt.k2_sub = false; }      // the overflow rerun: plain K2
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
@@ -620,6 +621,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
+    else if (k == "k2_sub") { ctx->opt.k2_sub = value != 0; }
     else if (k == "k2_warps") { if (value != 1 && value != 4) return BSW_EINVAL; ctx->k2_warps = (int)value; }
     else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
@@ -1029,7 +1031,7 @@ int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t*
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     size_t nl = 0;
     { int rc = enqueue_gather(ctx, s);                  // the device half of the scheduler is part of every pass
-      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl);
+      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl, ctx->opt.k2_sub);
       if (rc) { cudaSetDevice(prev); return rc; }
       if (s.plan.n_k1_tiles) ++nl; }
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));

@@ -51,6 +51,8 @@ __device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
     return (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
 }
 
+template <int NW> __device__ __forceinline__ void k2_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
+
 template <int GENERIC, int K2_WARPS>
 __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
 {
@@ -74,13 +76,16 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     int* xagg = reinterpret_cast<int*>(smem_raw + 16);                            // [K2_WARPS] group aggregate of pass 1
     int* xhl  = xagg + K2_WARPS;                                                  // [K2_WARPS] h of the group's last column
     int* xkey = xhl + K2_WARPS;                                                   // [K2_WARPS] per-warp arg-max key
-    uint32_t* qs = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);          // qcap/8 words (+ pad)
-    uint32_t* zb = qs + (qcap >> 3) + 4;                                          // rcap/32 words of zero bits
+    // Short queries are staged in shared memory by TMA; in ring mode (long queries) the packed query stays in the source
+    // arena: lane l of a group reads word (column >> 3), consecutive lanes read consecutive words, L1/L2 resident.
+    uint32_t* qsm = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);         // qcap/8 words (+ pad), unused in ring mode
+    const uint32_t* qs = ring ? (A.arena + (size_t)hd.qoff16 * 4u) : qsm;
+    uint32_t* zb = qsm + (ring ? 0 : (qcap >> 3)) + 4;                            // rcap/32 words of zero bits
     uint32_t* eh = zb + (rcap >> 5) + 4;                                          // rcap + 8 words
     eh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(eh) + 15) & ~(uintptr_t)15);
 
-    if (tid == 0) {
-        const uint32_t bar = k2_smem_u32(mbar), dst = k2_smem_u32(qs);
+    if (tid == 0 && !ring) {
+        const uint32_t bar = k2_smem_u32(mbar), dst = k2_smem_u32(qsm);
         const void* src = reinterpret_cast<const uint4*>(A.arena) + hd.qoff16;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         eh[j] = (uint32_t)hv;
     }
     __syncthreads();                                   // mbarrier init + first row visible to every warp
-    {
+    if (!ring) {
         const uint32_t bar = k2_smem_u32(mbar);
         uint32_t done = 0;
         while (!done) {
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 const uint4 wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
                 const uint4 wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
                 wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
-                const uint32_t qw = qs[jl >> 3];
+                const uint32_t qw = (jl >> 3) < nqw ? qs[jl >> 3] : 0u;
                 const uint32_t x = GENERIC ? qw : (qw ^ trep);
                 // pass 1: everything that does not need the incoming F
 #pragma unroll
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             } else if (lane == 31) {
                 xagg[warp] = 0;
             }
-            __syncthreads();                                               // (1) group aggregates visible
+            k2_sync<K2_WARPS>();                                           // (1) group aggregates visible
             // f entering this warp's group: the round's carry and the aggregates of the groups before it
             int cin = carry - e256 * warp;
             int cnext = carry - e256 * K2_WARPS;
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 }
                 if (lane == 31) xhl[warp] = h[7];
             }
-            __syncthreads();                                               // (2) last-column h of every group visible
+            k2_sync<K2_WARPS>();                                           // (2) last-column h of every group visible
             if (active) {
                 int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
                 if (lane == 0) hleft = (warp == 0) ? hcarry : xhl[warp - 1];
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         }
         key = __reduce_max_sync(0xffffffffu, key);
         if (lane == 0) xkey[warp] = key;
-        __syncthreads();                                                   // (3) row buffer, zero bits and keys visible
+        k2_sync<K2_WARPS>();                                               // (3) row buffer, zero bits and keys visible
 
         // ---- row epilogue (identical in every thread of the CTA) ----
         key = xkey[0];
@@ -293,7 +298,7 @@ size_t k2_smem_bytes(int qmax, int wmax)
     const size_t qcap = ((size_t)qmax + 1 + K2_GROUP - 1) & ~(size_t)(K2_GROUP - 1);
     const bool ring = qcap > (size_t)K2_RING && 2 * (size_t)wmax + 1 + 2 * K2_GROUP <= (size_t)K2_RING;
     const size_t rcap = ring ? (size_t)K2_RING : qcap;
-    return (size_t)K2_HDR_BYTES + ((qcap >> 3) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
+    return (size_t)K2_HDR_BYTES + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
 }
 
 template <int GENERIC, int NW>

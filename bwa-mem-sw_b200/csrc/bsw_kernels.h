@@ -29,6 +29,11 @@ size_t k3_smem_bytes(int qmax, int nqw_max);
 cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, cudaStream_t st);
 size_t k2_smem_bytes(int qmax, int wmax);
 
+// K2S: K2's algorithm with 8 lanes per task, four long tasks per warp (narrow live windows), row ring of a.ring_cols
+// columns; tasks whose window outgrows the ring come back with STATUS_OVERFLOW (the host reruns them on K2).
+cudaError_t k2s_launch(const LaunchArgs& a, int generic, cudaStream_t st);
+int k2s_ring_cols(int qmax, int wmax);
+
 // INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
 // streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.
 cudaError_t int_peak_run(double out_ops[5], double* sm_clock_mhz, int* sm_count, cudaStream_t st);

@@ -165,7 +165,7 @@ static inline size_t k2_task_smem(int qmax, int wmax)
     const size_t qcap = ((size_t)qmax + 1 + 255) & ~(size_t)255;
     const bool ring = qcap > 2048 && 2 * (size_t)wmax + 513 <= 2048;
     const size_t rcap = ring ? 2048 : qcap;
-    return 128 + ((qcap >> 3) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
+    return 128 + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
 }
 static inline int occupancy(size_t smem)
 {

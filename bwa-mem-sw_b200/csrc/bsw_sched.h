@@ -31,6 +31,8 @@ struct SchedOptions {
     int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
     int host_threads = 0;       // 0 = hardware concurrency (capped)
     bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
+    bool k2_sub = false;        // long tasks first run on K2S (8 lanes per task, small row ring; overflows rerun on K2).
+                                // Off by default: measured slower than K2 (the four sub-warps of a warp do not stay converged)
     bool ring = false;          // long V1 tasks whose first row fits run on K1R (ring row buffer in K1's lane function).
                                 // Off by default: measured slower than K2 (3 warps/SM with a 512-column ring), see DESIGN.md
     bool pair = false;          // V1 + FAST tasks run two per lane (K1P, packed int16x2).  Off by default: measured slower

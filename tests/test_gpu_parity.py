@@ -282,6 +282,17 @@ def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
     both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=82))          # default: K2 (one warp per task, ring row buffer)
     both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=83), opts={"k2_warps": 4})
     ctx.set_option("k2_warps", 1)
+    # K2S (option k2_sub): 8 lanes per task, 512-column ring, overflowing tasks rerun on K2
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=85), opts={"k2_sub": 1})
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=86, n_frac=0.02), opts={"k2_sub": 1, "force_kernel": 2})
+    rng = np.random.default_rng(6)
+    qs, ts = [], []
+    for k in range(12):                                       # near-perfect 3 kb matches: windows outgrow K2S's 512-column ring
+        q = rng.integers(0, 4, 3000).astype(np.uint8)
+        qs.append(q); ts.append(np.concatenate([q, q[:200]]).astype(np.uint8))
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    both(B, O, ctx, dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.full(12, 400, np.int32), w=np.full(12, 400, np.int32)), opts={"k2_sub": 1})
+    ctx.set_option("k2_sub", 0)
 
 
 def _k1r_cases(B, O, ctx):
