@@ -1026,7 +1026,6 @@ int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t*
     cudaGetDevice(&prev);
     CUDA_TRY(ctx, cudaSetDevice(R->dev));
     Slot& s = R->slot;
-    const Plan& P = s.plan;
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     size_t nl = 0;
