@@ -143,7 +143,8 @@ int grow_pinned(bsw_ctx* ctx, T** p, size_t* cap, size_t need)
     if (need <= *cap) return 0;
     if (*p) cudaFreeHost(*p);
     *p = nullptr; *cap = 0;
-    const size_t want = need + need / 4 + 64;
+    // generous headroom: chunks differ in size from call to call, and a pinned reallocation costs milliseconds
+    const size_t want = need + need / 2 + 65536 / sizeof(T) + 64;
     CUDA_TRY(ctx, cudaHostAlloc((void**)p, want * sizeof(T), cudaHostAllocDefault));
     *cap = want;
     return 0;
@@ -154,7 +155,7 @@ int grow_device(bsw_ctx* ctx, T** p, size_t* cap, size_t need)
     if (need <= *cap) return 0;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
-    const size_t want = need + need / 4 + 64;
+    const size_t want = need + need / 2 + 65536 / sizeof(T) + 64;
     CUDA_TRY(ctx, cudaMalloc((void**)p, want * sizeof(T)));
     *cap = want;
     return 0;
