@@ -38,8 +38,8 @@ double now_ms()
 // One staging slot = one in-flight chunk on one stream.
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaStream_t side[2] = { nullptr, nullptr };           // extra streams: the bucket launches of one big plan overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr };
+    cudaStream_t side[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // extra streams: the bucket launches of one big plan overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     // One pinned input block per chunk, mirrored on the device and moved with a single cudaMemcpyAsync:
     //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] ]   (16-byte aligned parts)
@@ -168,7 +168,7 @@ int slot_init(bsw_ctx* ctx, Slot& s)
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k1));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 5; ++k) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s.side[k], cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_join[k], cudaEventDisableTiming));
     }
@@ -190,7 +190,7 @@ void slot_free(Slot& s)
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-    for (int k = 0; k < 2; ++k) { if (s.ev_join[k]) cudaEventDestroy(s.ev_join[k]); if (s.side[k]) cudaStreamDestroy(s.side[k]); }
+    for (int k = 0; k < 5; ++k) { if (s.ev_join[k]) cudaEventDestroy(s.ev_join[k]); if (s.side[k]) cudaStreamDestroy(s.side[k]); }
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -235,17 +235,19 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
     const Plan& P = s.plan;
     size_t nl = 0;
     // A big plan has one launch per occupancy bucket; issued on one stream each bucket would wait for the previous
-    // bucket's last CTA.  Spread them over the slot's three streams (fork after the gather, join before the D2H).
+    // bucket's last CTA.  Spread them over the slot's four streams (fork after the gather, join before the D2H).
     const bool spread = P.launches.size() > 1 && P.tiles.size() >= 2048;
+    static const int nside = getenv("BSW_SIDE_STREAMS") ? std::max(0, std::min(5, atoi(getenv("BSW_SIDE_STREAMS")))) : 3;
     if (spread) {
         CUDA_TRY(ctx, cudaEventRecord(s.ev_fork, s.stream));
-        for (int k = 0; k < 2; ++k) CUDA_TRY(ctx, cudaStreamWaitEvent(s.side[k], s.ev_fork, 0));
+        for (int k = 0; k < nside; ++k) CUDA_TRY(ctx, cudaStreamWaitEvent(s.side[k], s.ev_fork, 0));
     }
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
         a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
-        cudaStream_t st = spread ? (nl % 3 == 0 ? s.stream : s.side[nl % 3 - 1]) : s.stream;
+        const size_t lane_ix = nl % (size_t)(nside + 1);
+        cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
                       : (L.kind == 3) ? k1p_launch(a, sym, st)
                       : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
@@ -255,7 +257,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         ++nl;
     }
     if (spread) {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < nside; ++k) {
             CUDA_TRY(ctx, cudaEventRecord(s.ev_join[k], s.side[k]));
             CUDA_TRY(ctx, cudaStreamWaitEvent(s.stream, s.ev_join[k], 0));
         }

@@ -205,6 +205,10 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
     for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[hist[key[t] >> 16]++] = t; }
 
+    // new occupancy bucket (= new launch) when a tile would fit at >= 1.15x the CTAs/SM of the current bucket (big plans;
+    // measured best with the launches spread over four streams) or >= 1.3x (small chunks: fewer launches per chunk)
+    static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
+    const int bucket_pct = bucket_env ? bucket_env : (n >= 65536 ? 115 : 130);
     // tiles
     const size_t nslot_bound = n + (size_t)4 * TILE_LANES;
     plan->slots.reserve(nslot_bound); plan->slot_src.reserve(nslot_bound); plan->slot_task.reserve(nslot_bound);
@@ -273,7 +277,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
             L.wmax = std::max(L.wmax, wmax);
             if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw_max; }
             else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw_max); }   // saturated sort key (very long tasks)
-            else if (!is_k2 && !is_ring && occ * 10 >= occ0 * 13) {      // K2 / K1R: one launch per class (measured: bucket tails cost more than occupancy gains)
+            else if (!is_k2 && !is_ring && occ * 100 >= occ0 * bucket_pct) {      // K2 / K1R: one launch per class (measured: bucket tails cost more than occupancy gains)
                 close_launch(L, (uint32_t)plan->tiles.size());
                 L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; L.wmax = wmax; occ0 = occ;
             }
