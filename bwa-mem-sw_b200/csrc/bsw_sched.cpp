@@ -208,7 +208,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     // new occupancy bucket (= new launch) when a tile would fit at >= 1.15x the CTAs/SM of the current bucket (big plans;
     // measured best with the launches spread over four streams) or >= 1.3x (small chunks: fewer launches per chunk)
     static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
-    const int bucket_pct = bucket_env ? bucket_env : (n >= 65536 ? 115 : 130);
+    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : 130);
     // tiles
     const size_t nslot_bound = n + (size_t)4 * TILE_LANES;
     plan->slots.reserve(nslot_bound); plan->slot_src.reserve(nslot_bound); plan->slot_task.reserve(nslot_bound);
