@@ -31,6 +31,10 @@ import numpy as np  # noqa: E402
 METRIC = "seed-extension GCUPS (cells_band; ksw_extend2 recurrence, bit-exact), tasks/s alongside"
 OPS_PER_CELL = 13            # 1 add, 4 sub, 7 max, 1 select
 FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per bench step (1 M x 150 bp), one ncu capture of this command
+# (profiles/r01_dram_bytes_k0_k1.csv): K0 gather 174.5 MB read + 65.5 MB written, the eight K1 launches 93.2 MB read, 0 written
+# (the 32 MB of results stay in L2 until the D2H copy)
+NCU_TRAFFIC = {"k0": 240.0e6, "k1": 93.2e6}
 
 
 def parse_args():
@@ -218,6 +222,7 @@ def main():
         cells_all, launches_all = float(cells), launches
     if rank == 0:
         steps = args.steps
+        default_wl = args.workload == "cfg2_150bp" and n == 1_000_000
         gcups = cells_all * steps / (dev_ms * 1e-3) * 1e-9
         e2e_gcups = cells_all * steps / e2e_s * 1e-9
         int_peak = peak["vimnmx_tops"]
@@ -243,12 +248,15 @@ def main():
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tops/s", "frac": achieved / int_peak,
-                         "traffic": None, "ops_per_cell": OPS_PER_CELL,
+                         "traffic": NCU_TRAFFIC["k1"] if default_wl else None, "traffic_unit": "bytes of DRAM per step, K1 launches (ncu)",
+                         "ops_per_cell": OPS_PER_CELL,
                          "peak_source": "bsw_measure_int_peak on this GPU: dependency-free VIMNMX stream (ALU pipe, where every max of the "
                                         "recurrence must issue); IADD3 %.2f, fused VIADDMNMX %.2f (2 ops/instr), IADD3+IMAD both pipes %.2f Tops/s at %.0f MHz"
                                         % (peak["iadd_tops"], peak["dpx_tops"], peak["dual_tops"], peak["sm_clock_mhz"])},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                             "traffic": None, "peak_source": hbm_src,
+                             "traffic": (NCU_TRAFFIC["k0"] + NCU_TRAFFIC["k1"]) if default_wl else None, "algorithmic_bytes": alg_bytes,
+                             "traffic_unit": "bytes of DRAM per step, K0 + K1 launches (ncu, profiles/r01_dram_bytes_k0_k1.csv)",
+                             "peak_source": hbm_src,
                              "note": "streaming evidence only: the path is compute-bound at ~1e3 int-ops per byte"},
         }
         if not args.no_cpu_baseline and world == 1:
