@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="bsw", choices=["bsw", "reference"])
     ap.add_argument("--workload", default="cfg2_150bp")
     ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=200_000, help="tasks of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="tasks of the CPU baseline sample (default: the whole batch, ~18 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -18,14 +18,17 @@ constexpr int K0_WARPS = 4;
 __device__ __forceinline__ void k0_copy_block(const uint4* __restrict__ src16, int own_words, uint32_t* __restrict__ dst,
                                               int tile_words, int lane)
 {
-    for (int m = 0; m * 4 < tile_words; ++m) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (m * 4 < own_words) v = __ldg(src16 + m);
+    // 32 bytes (one DRAM sector) per lane per step: a lane walks its own task, so a 16-byte step would fetch every
+    // sector twice
+    for (int m = 0; m * 4 < tile_words; m += 2) {
+        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+        if (m * 4 < own_words) v0 = __ldg(src16 + m);
+        if (m * 4 + 4 < own_words) v1 = __ldg(src16 + m + 1);
         uint32_t* d = dst + (size_t)(m * 4) * TILE_LANES + lane;
-        d[0] = v.x;
-        if (m * 4 + 1 < tile_words) d[TILE_LANES] = v.y;
-        if (m * 4 + 2 < tile_words) d[2 * TILE_LANES] = v.z;
-        if (m * 4 + 3 < tile_words) d[3 * TILE_LANES] = v.w;
+        const uint32_t w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (m * 4 + k < tile_words) d[k * TILE_LANES] = w[k];
     }
 }
 
