@@ -393,7 +393,19 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
-    const size_t chunk = std::max<size_t>(32, ctx->chunk_tasks);
+    // chunk size: chunk_tasks for short reads, fewer tasks per chunk when they are long (about 6 MB of bases per chunk),
+    // so that a batch of long tasks still spreads over all the host workers
+    size_t chunk = std::max<size_t>(32, ctx->chunk_tasks);
+    {
+        const size_t probe = std::min<size_t>(n, 512);
+        std::vector<ExtTask> pv(probe);
+        src.fill(src.self, 0, probe, pv.data());
+        uint64_t bases = 0;
+        for (const ExtTask& t : pv) bases += (uint64_t)std::max(t.qlen, 0) + (uint64_t)std::max(t.tlen, 0);
+        const size_t mean = (size_t)(bases / probe) + 1;
+        const size_t by_bytes = std::max<size_t>(64, (size_t)(6u << 20) / mean);
+        chunk = std::min(chunk, by_bytes);
+    }
     const size_t nchunks = (n + chunk - 1) / chunk;
     const size_t ndev = ctx->devs.size();
     size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
