@@ -71,6 +71,14 @@ def test_k2_long_reads(B, O, ctx):
     both(B, O, ctx, B.synth_tasks("cfg4_long", 48, seed=9), zdrop=400)
 
 
+def test_long_batch_spreads_over_chunks(B, O, ctx):
+    """Adaptive chunking: a batch of long tasks is cut by bases, not by task count, so several workers take part."""
+    t = B.synth_tasks("cfg4_long", 1500, seed=90)
+    ctx.reset_stats()
+    both(B, O, ctx, t)
+    assert ctx.stats()["kernel_launches"] >= 2          # more than one chunk
+
+
 def test_mixed_short_and_long_in_one_batch(B, O, ctx):
     a, b = B.synth_tasks("cfg3_mixed", 3000, seed=10), B.synth_tasks("cfg4_long", 8, seed=10)
     t = dict(qbuf=np.concatenate([a["qbuf"][:a["qoff"][-1]], b["qbuf"]]), tbuf=np.concatenate([a["tbuf"][:a["toff"][-1]], b["tbuf"]]),
