@@ -52,3 +52,31 @@ def oracle_chain2aln(O, B, params2, seeds, variant=1):
     out, cells = O.chain2aln_batch(oracle_params(O, params2), tasks, variant=variant)
     del keep
     return out, cells
+
+
+def random_small_tasks(rng, n, qmax=60, tmax=90):
+    """Adversarial little tasks: every combination of tiny / small h0, w, lengths, related / unrelated / repetitive targets."""
+    qs, ts, h0, w = [], [], [], []
+    for k in range(n):
+        ql = int(rng.integers(1, qmax + 1))
+        tl = int(rng.integers(1, tmax + 1))
+        mode = k % 5
+        if mode == 0:
+            q = rng.integers(0, 4, ql)
+            t = rng.integers(0, 4, tl)
+        elif mode == 1:                                  # low-complexity: many ties for the arg-max
+            q = rng.integers(0, 2, ql)
+            t = rng.integers(0, 2, tl)
+        else:
+            q = rng.integers(0, 4, ql)
+            t = np.resize(q, tl)
+            flips = rng.random(tl) < (0.03 if mode == 2 else 0.2)
+            t = np.where(flips, (t + rng.integers(1, 4, tl)) % 4, t)
+            if mode == 4 and tl > 6:                     # an indel
+                c = int(rng.integers(1, tl - 2))
+                t = np.concatenate([t[:c], t[c + int(rng.integers(1, 3)):], rng.integers(0, 4, 2)])[:tl]
+        qs.append(q.astype(np.uint8)); ts.append(np.asarray(t).astype(np.uint8))
+        h0.append(int(rng.choice([1, 2, 3, 5, 8, 13, 21, 40, 90])))
+        w.append(int(rng.choice([0, 1, 2, 3, 5, 10, 30, 100])))
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    return dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))

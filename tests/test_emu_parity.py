@@ -130,3 +130,28 @@ def test_ring_overflow_is_reported(B, O):
         assert cells[0] == 0xffffffff and res["score"][0] == -999
     finally:
         flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 1, 384, 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_randomised_small_tasks(B, O, seed):
+    """Thousands of adversarial little tasks (h0 down to 1, w down to 0, ties, indels) under random scoring, both variants,
+    through K1, K1P and K1R lane functions."""
+    from helpers import random_small_tasks
+    rng = np.random.default_rng(1000 + seed)
+    t = random_small_tasks(rng, 3000)
+    pks = [dict(), dict(o_del=int(rng.integers(0, 6)), e_del=int(rng.integers(1, 4)), o_ins=int(rng.integers(0, 6)), e_ins=int(rng.integers(1, 4)),
+                     zdrop=int(rng.choice([0, 3, 10, 100])), a=int(rng.integers(1, 4)), b=int(rng.integers(1, 6)), end_bonus=int(rng.integers(0, 8)))]
+    for pk in pks:
+        for variant in (1, 2):
+            run_both(B, O, t, variant=variant, **pk)
+        flags = _emu_flags(B, pair=0, force_kernel=0, k2_min_qlen=0, ring=0)
+        flags["pair"].value = 1
+        try:
+            run_both(B, O, t, **pk)
+        finally:
+            flags["pair"].value = 0
+        flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 0, 8, 1
+        try:
+            run_both(B, O, t, **pk)
+        finally:
+            flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 1, 384, 0

@@ -317,3 +317,39 @@ def _k1r_cases(B, O, ctx):
     t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
     both(B, O, ctx, t)
     both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=84))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
+    """Adversarial little tasks (h0 down to 1, w down to 0, ties, indels), random scoring, through K1, K1P, K1R, K2 (1 and 4
+    warps), K2S and the fused level 2."""
+    from helpers import random_small_tasks
+    rng = np.random.default_rng(2000 + seed)
+    t = random_small_tasks(rng, 4000)
+    pk = dict(o_del=int(rng.integers(0, 6)), e_del=int(rng.integers(1, 4)), o_ins=int(rng.integers(0, 6)), e_ins=int(rng.integers(1, 4)),
+              zdrop=int(rng.choice([0, 3, 10, 100])), a=int(rng.integers(1, 4)), b=int(rng.integers(1, 6)), end_bonus=int(rng.integers(0, 8)))
+    for p in (dict(), pk):
+        both(B, O, ctx, t, **p)
+        both(B, O, ctx, t, variant=2, **p)
+        both(B, O, ctx, t, opts={"k1_pair": 1}, **p); ctx.set_option("k1_pair", 0)
+        both(B, O, ctx, t, opts={"ring": 1, "k2_min_qlen": 8}, **p); ctx.set_option("ring", 0)
+        both(B, O, ctx, t, opts={"force_kernel": 2}, **p)
+        both(B, O, ctx, t, opts={"force_kernel": 2, "k2_warps": 4}, **p); ctx.set_option("k2_warps", 1)
+        both(B, O, ctx, t, opts={"force_kernel": 2, "k2_sub": 1}, **p); ctx.set_option("k2_sub", 0)
+    # level 2 on random flank pairs
+    n = 2000
+    seeds = []
+    for r in range(n // 2):
+        l, g = 2 * r, 2 * r + 1
+        sl = lambda a, off, i: a[off[i]:off[i + 1]]
+        ql, tl, qr, tr = sl(t["qbuf"], t["qoff"], l), sl(t["tbuf"], t["toff"], l), sl(t["qbuf"], t["qoff"], g), sl(t["tbuf"], t["toff"], g)
+        if r % 5 == 1:
+            ql, tl = ql[:0], tl[:0]
+        if r % 5 == 2:
+            qr, tr = qr[:0], tr[:0]
+        h0 = int(t["h0"][l])
+        seeds.append(dict(q_left=ql, q_right=qr, t_left=tl, t_right=tr, init_score=(h0 if len(ql) == 0 else -1), qbeg=len(ql), h0=h0, id=r))
+    for w in (3, 100):
+        P2 = B.make_params2(B.make_params(**pk), w=w, pen_clip5=int(rng.integers(0, 8)), pen_clip3=int(rng.integers(0, 8)))
+        want, _ = oracle_chain2aln(O, B, P2, seeds)
+        assert_same(want, ctx.proc_element_batch(P2, seeds), "fused level 2")
