@@ -179,22 +179,30 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 }
                 const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
                 fin0 = (lane > 0) ? imax(Pex - e8 * (lane - 1), 0) : 0;    // f entering this lane if the group's carry-in were 0
-                if (lane == 31) xagg[warp] = imax(run, fin0 - e8);         // f leaving the group (zero carry-in)
-            } else if (lane == 31) {
+                if (K2_WARPS > 1 && lane == 31) xagg[warp] = imax(run, fin0 - e8);     // f leaving the group (zero carry-in)
+            } else if (K2_WARPS > 1 && lane == 31) {
                 xagg[warp] = 0;
             }
-            k2_sync<K2_WARPS>();                                           // (1) group aggregates visible
-            // f entering this warp's group: the round's carry and the aggregates of the groups before it
-            int cin = carry - e256 * warp;
-            int cnext = carry - e256 * K2_WARPS;
+            int cin;
+            if (K2_WARPS == 1) {
+                // one warp per task: the round's carry stays in registers (a group is always active here)
+                cin = imax(carry, 0);
+                const int fout = imax(run, imax(fin0, cin - e8 * lane) - e8);
+                carry = __shfl_sync(0xffffffffu, fout, 31);
+            } else {
+                k2_sync<K2_WARPS>();                                       // (1) group aggregates visible
+                // f entering this warp's group: the round's carry and the aggregates of the groups before it
+                cin = carry - e256 * warp;
+                int cnext = carry - e256 * K2_WARPS;
 #pragma unroll
-            for (int g = 0; g < K2_WARPS; ++g) {
-                const int ag = xagg[g];
-                if (g < warp) cin = imax(cin, ag - e256 * (warp - 1 - g));
-                cnext = imax(cnext, ag - e256 * (K2_WARPS - 1 - g));
+                for (int g = 0; g < K2_WARPS; ++g) {
+                    const int ag = xagg[g];
+                    if (g < warp) cin = imax(cin, ag - e256 * (warp - 1 - g));
+                    cnext = imax(cnext, ag - e256 * (K2_WARPS - 1 - g));
+                }
+                cin = imax(cin, 0);
+                carry = imax(cnext, 0);
             }
-            cin = imax(cin, 0);
-            carry = imax(cnext, 0);
 
             int h[8];
             uint32_t enew[8];
@@ -214,12 +222,13 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                         zbits |= (h[k] == 0 ? 1u : 0u) << k;
                     }
                 }
-                if (lane == 31) xhl[warp] = h[7];
+                if (K2_WARPS > 1 && lane == 31) xhl[warp] = h[7];
             }
-            k2_sync<K2_WARPS>();                                           // (2) last-column h of every group visible
+            if (K2_WARPS > 1) k2_sync<K2_WARPS>();                         // (2) last-column h of every group visible
             if (active) {
                 int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
-                if (lane == 0) hleft = (warp == 0) ? hcarry : xhl[warp - 1];
+                if (lane == 0) hleft = (K2_WARPS == 1 || warp == 0) ? hcarry : xhl[warp - 1];
+                if (K2_WARPS == 1) hcarry = __shfl_sync(0xffffffffu, h[7], 31);
                 if (full) {
                     // interior lane: columns jl..jl+7 are all cells of this row
                     uint4 oa, ob;
@@ -240,16 +249,18 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 }
                 reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
             }
-            hcarry = xhl[K2_WARPS - 1];          // only consumed when another round follows (then the last warp was active)
+            if (K2_WARPS > 1) hcarry = xhl[K2_WARPS - 1];      // only consumed when another round follows (then the last warp was active)
         }
         key = __reduce_max_sync(0xffffffffu, key);
-        if (lane == 0) xkey[warp] = key;
+        if (K2_WARPS > 1 && lane == 0) xkey[warp] = key;
         k2_sync<K2_WARPS>();                                               // (3) row buffer, zero bits and keys visible
 
         // ---- row epilogue (identical in every thread of the CTA) ----
-        key = xkey[0];
+        if (K2_WARPS > 1) {
+            key = xkey[0];
 #pragma unroll
-        for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
+            for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
+        }
         const int m = key >> 16, mj = key & 0xffff;
         cells += (unsigned long long)(lim - j0);
         const int h1 = (int)(eh[lim & rm] & 0xffffu);
