@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# libbsw.so's host pipeline drives ~100 streams: ask the driver for 32 hardware queues before any CUDA context exists
+# (the bsw_b200 package sets the same default on import; torch would otherwise create the context first)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 

@@ -21,6 +21,10 @@ import subprocess
 
 import numpy as np
 
+# libbsw.so's host pipeline keeps ~100 streams busy; more hardware queues than the default 8 avoids false dependencies
+# between them.  The driver reads this when the CUDA context is created, so set it before anything touches the GPU.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libbsw.so")

@@ -58,6 +58,7 @@ struct Slot {
     unsigned long long* h_cells = nullptr;
     // in-flight bookkeeping
     bool busy = false, timed = false;
+    double trace_ms[3] = { 0, 0, 0 };     // pack, plan, enqueue time of the last submit (BSW_TRACE)
     Plan plan;
     size_t first = 0, count = 0;     // chunk = tasks [first, first+count) of the batch
     size_t nlaunch = 0;
@@ -72,7 +73,7 @@ struct Slot {
 struct Worker {
     int dev = 0;
     bool ready = false;
-    Slot slots[2];
+    std::vector<Slot> slots;         // stream slots the worker cycles through (bsw_ctx::slots_per_worker)
 };
 
 struct Device {
@@ -93,7 +94,8 @@ struct bsw_ctx {
     std::vector<std::unique_ptr<Worker>> workers;
     int streams_per_device = 2;
     SchedOptions opt;
-    size_t chunk_tasks = 32768;
+    size_t chunk_tasks = 16384;
+    int slots_per_worker = 2;      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     bool kernel_timing = true;     // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms)
@@ -234,9 +236,10 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
 {
     const Plan& P = s.plan;
     size_t nl = 0;
-    // A big plan has one launch per occupancy bucket; issued on one stream each bucket would wait for the previous
-    // bucket's last CTA.  Spread them over the slot's four streams (fork after the gather, join before the D2H).
-    const bool spread = P.launches.size() > 1 && P.tiles.size() >= 2048;
+    // A plan has one launch per class and occupancy bucket; issued on one stream each would wait for the previous
+    // launch's last CTA (0.2-0.4 ms of tile latency each, measured 1.0 ms -> 0.38 ms for a 32 k task chunk).  Spread
+    // them over the slot's four streams (fork after the gather, join before the D2H).
+    const bool spread = P.launches.size() > 1;
     static const int nside = getenv("BSW_SIDE_STREAMS") ? std::max(0, std::min(5, atoi(getenv("BSW_SIDE_STREAMS")))) : 3;
     if (spread) {
         CUDA_TRY(ctx, cudaEventRecord(s.ev_fork, s.stream));
@@ -329,6 +332,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     if (P.n_k1_tiles) ++s.nlaunch;
     st->validate_ms += t1 - t0;
     st->pack_ms += t2 - t1;
+    s.trace_ms[0] = t1 - t0; s.trace_ms[1] = t2 - t1; s.trace_ms[2] = now_ms() - t2;
     st->h2d += s.in_bytes;
     st->d2h += nslots * sizeof(SlotResult);
     st->launches += s.nlaunch;
@@ -405,6 +409,9 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         const size_t mean = (size_t)(bases / probe) + 1;
         const size_t by_bytes = std::max<size_t>(64, (size_t)(6u << 20) / mean);
         chunk = std::min(chunk, by_bytes);
+        // a batch smaller than threads x chunk: still one chunk per worker (not below 2048 tasks: launch overheads)
+        const size_t per_worker = (n + (size_t)opt.host_threads - 1) / (size_t)opt.host_threads;
+        chunk = std::min(chunk, std::max<size_t>(2048, (per_worker + 31) & ~(size_t)31));
     }
     const size_t nchunks = (n + chunk - 1) / chunk;
     const size_t ndev = ctx->devs.size();
@@ -413,7 +420,26 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     if (nworkers < 1) nworkers = 1;
     for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
 
-    std::atomic<size_t> next(0);
+    // Guided self-scheduling: a worker takes remaining/(guide*workers) tasks, at most `chunk` and at least chunk/4 --
+    // big chunks while there is plenty of work (few launches, well-filled GPU), small ones near the end so that the
+    // work still on the GPU after the last chunk is packed (the un-overlapped tail of the call) is short.
+    // Measured on 1 M x 150 bp: shrinking chunks cost more (launches, copies) than the shorter tail saves, so the default
+    // (min_div 1) is fixed-size chunks; BSW_GUIDE / BSW_MIN_DIV keep the experiment reachable.
+    static const size_t guide = getenv("BSW_GUIDE") ? (size_t)std::max(1, atoi(getenv("BSW_GUIDE"))) : 1;
+    static const size_t min_div = getenv("BSW_MIN_DIV") ? (size_t)std::max(1, atoi(getenv("BSW_MIN_DIV"))) : 1;
+    const size_t min_chunk = std::max<size_t>(32, chunk / min_div);
+    std::atomic<size_t> cursor(0);
+    auto grab = [&](size_t* first, size_t* count) -> bool {
+        size_t cur = cursor.load(std::memory_order_relaxed);
+        for (;;) {
+            if (cur >= n) return false;
+            const size_t rem = n - cur;
+            size_t c = std::min(chunk, std::max(min_chunk, rem / (guide * nworkers)));
+            c = (c + 31) & ~(size_t)31;
+            if (c > rem || rem - c < min_chunk / 2) c = rem;
+            if (cursor.compare_exchange_weak(cur, cur + c, std::memory_order_relaxed)) { *first = cur; *count = c; return true; }
+        }
+    };
     std::atomic<int> first_err(0);
     std::mutex stat_mu;
     LocalStats total;
@@ -425,34 +451,37 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         std::vector<size_t> ovf;
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
-        if (!r && !W.ready) {
-            for (Slot& s : W.slots) if (!r) r = slot_init(ctx, s);
-            W.ready = (r == 0);
+        if (!r && W.slots.size() < (size_t)ctx->slots_per_worker) {
+            const size_t have = W.slots.size();
+            W.slots.resize((size_t)ctx->slots_per_worker);
+            for (size_t q = have; q < W.slots.size() && !r; ++q) r = slot_init(ctx, W.slots[q]);
         }
-        int cur = 0;
+        const size_t nslot = (size_t)ctx->slots_per_worker;
+        size_t cur = 0;
         const bool trace = getenv("BSW_TRACE") != nullptr;
         std::string tr;
         auto T = [&]() { return now_ms() - w0; };
         if (trace) tr += "w" + std::to_string(k) + " start " + std::to_string(T()) + "\n";
         while (!r && !first_err.load(std::memory_order_relaxed)) {
-            const size_t c = next.fetch_add(1);
-            if (c >= nchunks) break;
+            size_t first = 0, count = 0;
+            if (!grab(&first, &count)) break;
             Slot& s = W.slots[cur];
-            cur ^= 1;
+            cur = (cur + 1) % nslot;
             const double c0 = T();
             if ((r = slot_collect(ctx, s, out, cells, &st, &ovf))) break;
-            if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(c) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
-            const size_t first = c * chunk, count = std::min(chunk, n - first);
+            if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(first) + "+" + std::to_string(count) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
             const double v0 = now_ms();
             s.tasks.resize(count);
             src.fill(src.self, first, count, s.tasks.data());
             st.validate_ms += now_ms() - v0;
             const double f1 = T();
             r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st);
-            if (trace) tr += " fill.." + std::to_string(f1) + " submitted " + std::to_string(T()) + "\n";
+            if (trace) tr += " fill.." + std::to_string(f1) + " submitted " + std::to_string(T()) + " (pack " + std::to_string(s.trace_ms[0]) +
+                             " plan " + std::to_string(s.trace_ms[1]) + " api " + std::to_string(s.trace_ms[2]) + ")\n";
         }
         if (trace) tr += "w" + std::to_string(k) + " drain " + std::to_string(T());
-        for (Slot& s : W.slots) {
+        for (size_t q = 0; q < W.slots.size(); ++q) {                                    // oldest chunk first
+            Slot& s = W.slots[(cur + q) % W.slots.size()];
             if (r) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }    // leave the device quiescent
             else r = slot_collect(ctx, s, out, cells, &st, &ovf);
         }
@@ -515,14 +544,15 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
 
 // ---- task sources ----
 struct FlatSrc {
-    const bsw_params* p; const uint8_t* qbuf; const int64_t* qoff; const uint8_t* tbuf; const int64_t* toff;
+    const bsw_params* p; const BandClamp* clamp; const uint8_t* qbuf; const int64_t* qoff; const uint8_t* tbuf; const int64_t* toff;
     const int32_t* h0; const int32_t* w;
 };
 void fill_flat(const void* self, size_t first, size_t count, ExtTask* out)
 {
     const FlatSrc& S = *static_cast<const FlatSrc*>(self);
     const bsw_params* p = S.p;
-    int last_q = -1, last_w = -1, last_c = -1;
+    const BandClamp& clamp = *S.clamp;
+    (void)p;
     for (size_t k = 0; k < count; ++k) {
         const size_t i = first + k;
         ExtTask& x = out[k];
@@ -531,25 +561,18 @@ void fill_flat(const void* self, size_t first, size_t count, ExtTask* out)
         x.qlen = (ql < 0 || ql > 0x7fffffff) ? -1 : (int32_t)ql;
         x.tlen = (tl < 0 || tl > 0x7fffffff) ? -1 : (int32_t)tl;
         x.h0 = S.h0[i];
-        if (x.qlen >= 1 && S.w[i] >= 0) {
-            if (x.qlen != last_q || S.w[i] != last_w) {
-                last_q = x.qlen; last_w = S.w[i];
-                last_c = clamp_band(p->mat, x.qlen, S.w[i], p->end_bonus, p->o_ins, p->e_ins, p->o_del, p->e_del);
-            }
-            x.w = last_c;
-        } else x.w = -1;
+        x.w = (x.qlen >= 1 && S.w[i] >= 0) ? clamp(x.qlen, S.w[i]) : -1;
     }
 }
-struct RecSrc { const bsw_params* p; const bsw_task* tasks; };
+struct RecSrc { const bsw_params* p; const BandClamp* clamp; const bsw_task* tasks; };
 void fill_records(const void* self, size_t first, size_t count, ExtTask* out)
 {
     const RecSrc& S = *static_cast<const RecSrc*>(self);
-    const bsw_params* p = S.p;
     for (size_t k = 0; k < count; ++k) {
         const bsw_task& t = S.tasks[first + k];
         ExtTask& x = out[k];
         x.q = t.query; x.t = t.target; x.qlen = t.qlen; x.tlen = t.tlen; x.h0 = t.h0;
-        x.w = (t.qlen >= 1 && t.w >= 0) ? clamp_band(p->mat, t.qlen, t.w, p->end_bonus, p->o_ins, p->e_ins, p->o_del, p->e_del) : -1;
+        x.w = (t.qlen >= 1 && t.w >= 0) ? (*S.clamp)(t.qlen, t.w) : -1;
     }
 }
 void fill_vector(const void* self, size_t first, size_t count, ExtTask* out)
@@ -569,6 +592,10 @@ int bsw_init(bsw_ctx** out, const int* device_ids, int n_devices, int streams_pe
 {
     if (!out) return BSW_EINVAL;
     *out = nullptr;
+    // Every worker slot owns streams; with the default 8 hardware queues their launches falsely serialise (measured:
+    // e2e 9.2 -> 8.3 ms on 1 M tasks with 32).  Read by the driver when the context is created, so this only takes
+    // effect if no CUDA context exists yet in the process; a value set by the user wins.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev_avail = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev_avail);
     if (e != cudaSuccess || ndev_avail <= 0) return BSW_ECUDA;       // no CPU fallback: no device, no context
@@ -634,6 +661,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     const std::string k(key);
     if (k == "variant") { if (value != 1 && value != 2) return BSW_EINVAL; ctx->opt.variant = (int)value; }
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
+    else if (k == "slots") { if (value < 1 || value > 16) return BSW_EINVAL; ctx->slots_per_worker = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
     else if (k == "k2_sub") { ctx->opt.k2_sub = value != 0; }
@@ -653,7 +681,8 @@ int bsw_extend_batch(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tas
     if (n == 0) return BSW_OK;
     if (!params || !tasks || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
-    const RecSrc S{ params, tasks };
+    const BandClamp clamp(params->mat, params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del);
+    const RecSrc S{ params, &clamp, tasks };
     return run_extensions(ctx, params, TaskSource{ &S, fill_records }, n, out, nullptr);
 }
 
@@ -665,7 +694,8 @@ int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t*
     if (n == 0) return BSW_OK;
     if (!params || !qbuf || !qoff || !tbuf || !toff || !h0 || !w || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
-    const FlatSrc S{ params, qbuf, qoff, tbuf, toff, h0, w };
+    const BandClamp clamp(params->mat, params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del);
+    const FlatSrc S{ params, &clamp, qbuf, qoff, tbuf, toff, h0, w };
     return run_extensions(ctx, params, TaskSource{ &S, fill_flat }, n, out, cells);
 }
 
@@ -880,16 +910,18 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         Worker& W = *ctx->workers[k];
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
-        if (!r && !W.ready) {
-            for (Slot& sl : W.slots) if (!r) r = slot_init(ctx, sl);
-            W.ready = (r == 0);
+        if (!r && W.slots.size() < (size_t)ctx->slots_per_worker) {
+            const size_t have = W.slots.size();
+            W.slots.resize((size_t)ctx->slots_per_worker);
+            for (size_t q = have; q < W.slots.size() && !r; ++q) r = slot_init(ctx, W.slots[q]);
         }
-        int cur = 0;
+        const size_t nslot = (size_t)ctx->slots_per_worker;
+        size_t cur = 0;
         while (!r && !first_err.load(std::memory_order_relaxed)) {
             const size_t c = next.fetch_add(1);
             if (c >= nchunks) break;
             Slot& sl = W.slots[cur];
-            cur ^= 1;
+            cur = (cur + 1) % nslot;
             const double t0 = now_ms();
             if ((r = collect(sl))) break;
             const size_t first = c * chunk;

@@ -60,40 +60,49 @@ int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, 
 }
 
 // ---- packing: 16 bases per SSE2 op, validation fused ----
-// 8 bases (one per byte, codes 0..4) -> 8 nibbles, first base in the low nibble
-static inline uint32_t pack8(uint64_t x)
-{
-    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
-    x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
-    x = (x | (x >> 16)) & 0x00000000ffffffffull;
-    return (uint32_t)x;
-}
-
 // Packs `len` bases into dst (ceil(len/8) words, then zero-padded to a multiple of 4 words).  Returns the number of
-// words written (multiple of 4); *any4 / *ok accumulate "some base == 4" / "all bases <= 4" (bytewise masks).
-static inline int pack_seq16(const uint8_t* s, int len, uint32_t* dst, __m128i* any4, __m128i* ok)
+// words written (multiple of 4); *mx accumulates the bytewise maximum of the codes (validation: max <= 4, and max == 4
+// <=> the task holds an N), so the check costs one op per 16 bases.
+alignas(16) static const uint8_t k_tail_mask[32] = { 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
+                                                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+static inline __m128i nib16(__m128i x, __m128i lowbyte)
 {
-    const __m128i four = _mm_set1_epi8(4), lowbyte = _mm_set1_epi16(0x00ff);
+    // per 16-bit lane {b1,b0} -> b0 | b1<<4 in the low byte
+    return _mm_and_si128(_mm_or_si128(x, _mm_srli_epi16(x, 4)), lowbyte);
+}
+static inline int pack_seq16(const uint8_t* s, int len, uint32_t* dst, __m128i* mx)
+{
+    const __m128i lowbyte = _mm_set1_epi16(0x00ff);
+    __m128i m = *mx;
     int k = 0, done = 0;
-    for (; done + 16 <= len; done += 16, k += 2) {
-        const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done));
-        *any4 = _mm_or_si128(*any4, _mm_cmpeq_epi8(x, four));
-        *ok = _mm_and_si128(*ok, _mm_cmpeq_epi8(_mm_max_epu8(x, four), four));           // x <= 4 (unsigned)
-        // per 16-bit lane {b1,b0} -> b0 | b1<<4, then narrow the lanes to bytes
-        const __m128i y = _mm_and_si128(_mm_or_si128(x, _mm_srli_epi16(x, 4)), lowbyte);
-        _mm_storel_epi64(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(y, y));
+    for (; done + 32 <= len; done += 32, k += 4) {
+        const __m128i x0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done));
+        const __m128i x1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done + 16));
+        m = _mm_max_epu8(m, _mm_max_epu8(x0, x1));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(nib16(x0, lowbyte), nib16(x1, lowbyte)));
     }
-    if (done < len) {                                  // tail of 1..15 bases through a zero-padded 16-byte buffer
-        alignas(16) uint8_t buf[16] = { 0 };
-        memcpy(buf, s + done, (size_t)(len - done));
-        const __m128i x = _mm_load_si128(reinterpret_cast<const __m128i*>(buf));
-        *any4 = _mm_or_si128(*any4, _mm_cmpeq_epi8(x, four));
-        *ok = _mm_and_si128(*ok, _mm_cmpeq_epi8(_mm_max_epu8(x, four), four));
-        const __m128i y = _mm_and_si128(_mm_or_si128(x, _mm_srli_epi16(x, 4)), lowbyte);
-        _mm_storel_epi64(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(y, y));
-        k += 2;
+    // the last 1..31 bases: two 16-byte loads masked to the sequence.  Reading past the end is harmless as long as the
+    // load stays inside the page of a byte we own; next to a page end the bytes go through a bounce buffer instead.
+    const int rem = len - done;
+    if (rem > 0) {
+        __m128i x0, x1;
+        if (((uintptr_t)(s + done) & 4095u) <= 4096u - 32u) {
+            x0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done));
+            x1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done + 16));
+        } else {
+            alignas(16) uint8_t buf[32];
+            for (int j = 0; j < 32; ++j) buf[j] = j < rem ? s[done + j] : 0;
+            x0 = _mm_load_si128(reinterpret_cast<const __m128i*>(buf));
+            x1 = _mm_load_si128(reinterpret_cast<const __m128i*>(buf + 16));
+        }
+        const int r0 = rem < 16 ? rem : 16, r1 = rem - r0;
+        x0 = _mm_and_si128(x0, _mm_loadu_si128(reinterpret_cast<const __m128i*>(k_tail_mask + 16 - r0)));
+        x1 = _mm_and_si128(x1, _mm_loadu_si128(reinterpret_cast<const __m128i*>(k_tail_mask + 16 - r1)));
+        m = _mm_max_epu8(m, _mm_max_epu8(x0, x1));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(nib16(x0, lowbyte), nib16(x1, lowbyte)));
+        k += 4;
     }
-    if (k & 2) { dst[k] = 0; dst[k + 1] = 0; k += 2; }
+    *mx = m;
     return k;
 }
 
@@ -120,13 +129,14 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
         else if ((int64_t)t.h0 + (int64_t)t.qlen * max_mat > SCORE_CAP || t.qlen > K2_QLEN_CAP || t.tlen > 500000) e = BSW_ERANGE;
         uint8_t c = 0;
         if (!e) {
-            __m128i any4 = _mm_setzero_si128(), ok = _mm_set1_epi8((char)0xff);
+            __m128i mx = _mm_setzero_si128();
             src[i].qoff16 = (uint32_t)(w >> 2);
-            w += (size_t)pack_seq16(t.q, t.qlen, arena + w, &any4, &ok);
+            w += (size_t)pack_seq16(t.q, t.qlen, arena + w, &mx);
             src[i].toff16 = (uint32_t)(w >> 2);
-            w += (size_t)pack_seq16(t.t, t.tlen, arena + w, &any4, &ok);
-            if (_mm_movemask_epi8(ok) != 0xffff) e = BSW_EINVAL;
-            if (_mm_movemask_epi8(any4) || !opt.fast_matrix) c |= 1;
+            w += (size_t)pack_seq16(t.t, t.tlen, arena + w, &mx);
+            const __m128i four = _mm_set1_epi8(4);
+            if (_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_max_epu8(mx, four), four)) != 0xffff) e = BSW_EINVAL;     // some code > 4
+            if (_mm_movemask_epi8(_mm_cmpeq_epi8(mx, four)) || !opt.fast_matrix) c |= 1;                       // some code == 4
             bool longtask = opt.force_kernel == 2 || (opt.force_kernel == 0 && t.qlen >= opt.k2_min_qlen) || t.qlen > k1cap;
             if (opt.variant == 2) {               // K2 implements the V1 recurrence only
                 longtask = false;
@@ -150,6 +160,29 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
     for (int k = 0; k < 8; ++k) arena[w + (size_t)k] = 0;     // slack: the gather may read one 16-byte unit past a sequence
     *words_used = w + 8;
     return 0;
+}
+
+// order[] = task indices by ascending 32-bit key (stable LSD radix).  The digit width follows the chunk size: three
+// 11-bit passes for the usual 8-32 k task chunk (the three histograms come from one pass over the keys and stay in
+// L1), two 16-bit passes for big plans (resident batches) where the per-pass traffic dominates.
+static void radix_order(const uint32_t* key, size_t n, std::vector<uint32_t>& order, std::vector<uint32_t>& tmp, std::vector<uint32_t>& hist)
+{
+    if (n > ((size_t)1 << 17)) {
+        hist.assign(2 * 65537, 0);
+        uint32_t* h0 = hist.data(); uint32_t* h1 = h0 + 65537;
+        for (size_t i = 0; i < n; ++i) { ++h0[(key[i] & 0xffffu) + 1]; ++h1[(key[i] >> 16) + 1]; }
+        for (size_t b = 0; b < 65536; ++b) { h0[b + 1] += h0[b]; h1[b + 1] += h1[b]; }
+        for (size_t i = 0; i < n; ++i) tmp[h0[key[i] & 0xffffu]++] = (uint32_t)i;
+        for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[h1[key[t] >> 16]++] = t; }
+        return;
+    }
+    hist.assign(3 * 2049, 0);
+    uint32_t* h0 = hist.data(); uint32_t* h1 = h0 + 2049; uint32_t* h2 = h1 + 2049;
+    for (size_t i = 0; i < n; ++i) { const uint32_t k = key[i]; ++h0[(k & 2047u) + 1]; ++h1[((k >> 11) & 2047u) + 1]; ++h2[(k >> 22) + 1]; }
+    for (size_t b = 0; b < 2048; ++b) { h0[b + 1] += h0[b]; h1[b + 1] += h1[b]; h2[b + 1] += h2[b]; }
+    for (size_t i = 0; i < n; ++i) order[h0[key[i] & 2047u]++] = (uint32_t)i;
+    for (size_t i = 0; i < n; ++i) { const uint32_t t = order[i]; tmp[h1[(key[t] >> 11) & 2047u]++] = t; }
+    for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[h2[key[t] >> 22]++] = t; }
 }
 
 static inline size_t k1_tile_smem(int qmax, int nqw)
@@ -188,7 +221,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     // classes: 0 K1 fast, 1 K1 matrix, 2 K1R fast, 3 K1R matrix, 4 K2 fast, 5 K2 matrix
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
-    key.resize(n); order.resize(n); tmp.resize(n); hist.assign(65537, 0);
+    key.resize(n); order.resize(n); tmp.resize(n);
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& t = tasks[i];
         const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
@@ -196,22 +229,17 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
         const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
         key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
     }
-    // LSD radix, two 16-bit digits
-    for (size_t i = 0; i < n; ++i) ++hist[(key[i] & 0xffffu) + 1];
-    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
-    for (size_t i = 0; i < n; ++i) tmp[hist[key[i] & 0xffffu]++] = (uint32_t)i;
-    hist.assign(65537, 0);
-    for (size_t i = 0; i < n; ++i) ++hist[(key[i] >> 16) + 1];
-    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
-    for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[hist[key[t] >> 16]++] = t; }
+    radix_order(key.data(), n, order, tmp, hist);
 
     // new occupancy bucket (= new launch) when a tile would fit at >= 1.15x the CTAs/SM of the current bucket (big plans;
-    // measured best with the launches spread over four streams) or >= 1.3x (small chunks: fewer launches per chunk)
+    // measured best with the launches spread over four streams) or >= 2x (the chunks of the host pipeline: every extra
+    // launch and stream costs more there than the occupancy it buys -- e2e 8.0 -> 6.5 ms on 1 M x 150 bp)
     static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
-    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : 130);
+    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : 200);
     // tiles
-    const size_t nslot_bound = n + (size_t)4 * TILE_LANES;
+    const size_t nslot_bound = n + (size_t)8 * TILE_LANES;
     plan->slots.reserve(nslot_bound); plan->slot_src.reserve(nslot_bound); plan->slot_task.reserve(nslot_bound);
+    plan->tiles.reserve(n / TILE_LANES + 16);
     size_t arena16 = 0;     // tiled arena, in 16-byte units
     auto close_launch = [&](Launch& L, uint32_t tile_end) {
         L.ntiles = tile_end - L.tile0;
@@ -239,6 +267,24 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                 hd[sub].slot0 = (uint32_t)plan->slots.size();
                 int tq = 0, tt = 0;
                 const size_t lanes = is_k2 ? 1 : (size_t)TILE_LANES;
+                if (!is_pair && ntask == lanes) {
+                    // a full tile (the common case): write the 32 slots through raw pointers
+                    const size_t s0 = plan->slots.size();
+                    plan->slots.resize(s0 + lanes); plan->slot_src.resize(s0 + lanes); plan->slot_task.resize(s0 + lanes);
+                    SlotParam* sp = plan->slots.data() + s0; SlotSrc* ss = plan->slot_src.data() + s0; int64_t* st = plan->slot_task.data() + s0;
+                    const uint32_t* ord = order.data() + i;
+                    uint64_t cells = 0;
+                    for (size_t l = 0; l < lanes; ++l) {
+                        const uint32_t ti = ord[l];
+                        const ExtTask& t = tasks[ti];
+                        tq = std::max(tq, t.qlen); tt = std::max(tt, t.tlen); wmax = std::max(wmax, t.w);
+                        sp[l] = SlotParam{ t.qlen, t.tlen, t.h0, t.w };
+                        ss[l] = src[ti];
+                        st[l] = (int64_t)ti;
+                        cells += (uint64_t)(std::min<int64_t>(t.qlen, 2 * (int64_t)t.w + 1) * t.tlen);
+                    }
+                    plan->est_cells += cells;
+                } else
                 for (size_t l = 0; l < lanes; ++l) {
                     const size_t k = is_pair ? 2 * l + (size_t)sub : l;
                     if (k < ntask) {
@@ -304,7 +350,7 @@ void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* sr
     const size_t n = nseeds;
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
-    key.resize(n); order.resize(n); tmp.resize(n); hist.assign(65537, 0);
+    key.resize(n); order.resize(n); tmp.resize(n);
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& l = tasks[2 * i]; const ExtTask& r = tasks[2 * i + 1];
         const uint32_t g = ((cls[2 * i] | cls[2 * i + 1]) & 1u);
@@ -312,13 +358,7 @@ void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* sr
         const uint32_t qs = (uint32_t)std::min((l.qlen + r.qlen) >> 1, 1023), h = (uint32_t)std::min(l.h0 >> 1, 63);
         key[i] = (g << 30) | ((16383u - ql) << 16) | ((1023u - qs) << 6) | (63u - h);
     }
-    for (size_t i = 0; i < n; ++i) ++hist[(key[i] & 0xffffu) + 1];
-    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
-    for (size_t i = 0; i < n; ++i) tmp[hist[key[i] & 0xffffu]++] = (uint32_t)i;
-    hist.assign(65537, 0);
-    for (size_t i = 0; i < n; ++i) ++hist[(key[i] >> 16) + 1];
-    for (size_t b = 0; b < 65536; ++b) hist[b + 1] += hist[b];
-    for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[hist[key[t] >> 16]++] = t; }
+    radix_order(key.data(), n, order, tmp, hist);
 
     size_t arena16 = 0;
     auto close_launch = [&](Launch& L, uint32_t tile_end) {

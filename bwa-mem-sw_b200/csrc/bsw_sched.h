@@ -86,6 +86,24 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
 // sw_pe_array_proc_element.v:924-934 and applies them at sw_pe_array_sw_extend.v:1763-1765,1881,1890).
 int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, int e_ins, int o_del, int e_del);
 
+// The same clamp with the two divisions tabulated per query length (built once per call; short queries are the bulk).
+struct BandClamp {
+    static constexpr int TABLE = 1024;
+    int8_t mat[25]; int end_bonus, o_ins, e_ins, o_del, e_del;
+    int bound[TABLE + 1];
+    BandClamp(const int8_t m[25], int end_bonus_, int o_ins_, int e_ins_, int o_del_, int e_del_)
+        : end_bonus(end_bonus_), o_ins(o_ins_), e_ins(e_ins_), o_del(o_del_), e_del(e_del_)
+    {
+        for (int k = 0; k < 25; ++k) mat[k] = m[k];
+        for (int q = 0; q <= TABLE; ++q) bound[q] = clamp_band(mat, q, 0x7fffffff, end_bonus, o_ins, e_ins, o_del, e_del);
+    }
+    int operator()(int qlen, int w) const
+    {
+        if (qlen >= 0 && qlen <= TABLE) return w < bound[qlen] ? w : bound[qlen];
+        return clamp_band(mat, qlen, w, end_bonus, o_ins, e_ins, o_del, e_del);
+    }
+};
+
 // Simple fork-join helper.
 void parallel_for(size_t n, size_t grain, int nthreads, const void* ctx,
                   void (*fn)(const void* ctx, size_t lo, size_t hi));

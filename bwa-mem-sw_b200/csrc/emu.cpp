@@ -214,6 +214,7 @@ extern "C" int bsw_emu_host_phases(const bsw_params* params, const uint8_t* qbuf
     if (sc.size() < (size_t)threads) sc.resize((size_t)threads);
     std::atomic<size_t> next(0);
     std::atomic<int> slot(0);
+    const BandClamp clamp(params->mat, params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del);
     const double w0 = now();
     pfor((size_t)threads, 1, threads, [&](size_t, size_t) {
         Scratch& S = sc[(size_t)slot.fetch_add(1)];
@@ -224,14 +225,12 @@ extern "C" int bsw_emu_host_phases(const bsw_params* params, const uint8_t* qbuf
             const size_t first = c * chunk, cnt = std::min(chunk, n - first);
             double t0 = now();
             S.v.resize(cnt); S.cls.resize(cnt); S.ss.resize(cnt);
-            int last_q = -1, last_c = 0;
             for (size_t k = 0; k < cnt; ++k) {
                 const size_t i = first + k;
                 ExtTask& x = S.v[k];
                 x.q = qbuf + qoff[i]; x.t = tbuf + toff[i];
                 x.qlen = (int32_t)(qoff[i + 1] - qoff[i]); x.tlen = (int32_t)(toff[i + 1] - toff[i]); x.h0 = h0[i];
-                if (x.qlen != last_q) { last_q = x.qlen; last_c = clamp_band(params->mat, x.qlen, w[i], params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del); }
-                x.w = last_c;
+                x.w = clamp(x.qlen, w[i]);
             }
             double t1 = now();
             const size_t bound = source_arena_bound(S.v.data(), cnt);
