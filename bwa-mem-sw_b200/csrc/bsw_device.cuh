@@ -74,7 +74,8 @@ struct LaunchArgs {
     const TileHdr*   tiles;
     const SlotParam* slots;
     const uint32_t*  arena;        // K1: tiled arena; K2: source arena (16-byte aligned blocks)
-    SlotResult*      out;          // indexed by slot
+    SlotResult*      out;          // indexed by out_index[slot] (the chunk's task order), or by slot when out_index is null
+    const uint32_t*  out_index;
     unsigned long long* cells_total;   // device counter of evaluated DP cells (one atomic per warp), may be null
     DevParams        p;
     uint32_t         ntiles;

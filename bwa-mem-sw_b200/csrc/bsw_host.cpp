@@ -42,10 +42,10 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr, ev_join[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     // One pinned input block per chunk, mirrored on the device and moved with a single cudaMemcpyAsync:
-    //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] ]   (16-byte aligned parts)
+    //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] | u32 task-of-slot[] ]   (16-byte aligned parts)
     unsigned char* h_in = nullptr; size_t h_in_cap = 0;
     unsigned char* d_in = nullptr; size_t d_in_cap = 0;
-    size_t in_bytes = 0, off_tiles = 0, off_slots = 0, off_ssrc = 0;
+    size_t in_bytes = 0, off_tiles = 0, off_slots = 0, off_ssrc = 0, off_oidx = 0;
     SlotResult* h_out = nullptr;  size_t h_out_cap = 0;
     uint32_t* d_arena = nullptr;  size_t d_arena_cap = 0;     // tiled arena, written by the k0 gather kernel
     SlotResult* d_out = nullptr;  size_t d_out_cap = 0;
@@ -54,6 +54,7 @@ struct Slot {
     const TileHdr*   d_tiles() const { return reinterpret_cast<const TileHdr*>(d_in + off_tiles); }
     const SlotParam* d_slots() const { return reinterpret_cast<const SlotParam*>(d_in + off_slots); }
     const SlotSrc*   d_ssrc() const { return reinterpret_cast<const SlotSrc*>(d_in + off_ssrc); }
+    const uint32_t*  d_oidx() const { return reinterpret_cast<const uint32_t*>(d_in + off_oidx); }
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
     // in-flight bookkeeping
@@ -232,7 +233,7 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
 // Host statistics accumulated by one worker and merged once per call.
 struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0; };
 
-int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, bool k2_sub = true)
+int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, bool k2_sub, const uint32_t* out_index)
 {
     const Plan& P = s.plan;
     size_t nl = 0;
@@ -247,7 +248,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
     }
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
-        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out;
+        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
         const size_t lane_ix = nl % (size_t)(nside + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
@@ -290,7 +291,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     // upper bounds of the input block: nslots <= count + 4 classes * 31 padding lanes, tiles <= count + 4
     const size_t src_bound = source_arena_bound(s.tasks.data(), count) * 4;
     const size_t max_slots = count + 4 * TILE_LANES, max_tiles = count + 4;
-    const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc)) + 64;
+    const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc) + sizeof(uint32_t)) + 64;
     if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bound))) return rc;
     s.cls.resize(count); s.src.resize(count);
     size_t bad = 0; std::string msg;
@@ -308,24 +309,29 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     s.off_tiles = (s.src_words * 4 + 15) & ~(size_t)15;
     s.off_slots = s.off_tiles + P.tiles.size() * sizeof(TileHdr);
     s.off_ssrc = s.off_slots + nslots * sizeof(SlotParam);
-    s.in_bytes = s.off_ssrc + nslots * sizeof(SlotSrc);
+    s.off_oidx = s.off_ssrc + nslots * sizeof(SlotSrc);
+    s.in_bytes = s.off_oidx + nslots * sizeof(uint32_t);
     if (s.in_bytes > s.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); return BSW_ENOMEM; }
-    if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, nslots))) return rc;
+    if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, count))) return rc;
     if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
     if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.tiled_words))) return rc;
-    if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, nslots))) return rc;
+    if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, count))) return rc;      // results come back in task order
     memcpy(s.h_in + s.off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
     memcpy(s.h_in + s.off_slots, P.slots.data(), nslots * sizeof(SlotParam));
     memcpy(s.h_in + s.off_ssrc, P.slot_src.data(), nslots * sizeof(SlotSrc));
+    {
+        uint32_t* oi = reinterpret_cast<uint32_t*>(s.h_in + s.off_oidx);
+        for (size_t k = 0; k < nslots; ++k) oi[k] = (uint32_t)P.slot_task[k];      // padding lanes (-1) never write
+    }
     const double t2 = now_ms();
 
     // per chunk: 1 H2D, 1 gather, the bucket launches, 1 D2H, 1 event (the per-task cells come back in the records)
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if ((rc = enqueue_gather(ctx, s))) return rc;
-    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub, s.d_oidx()))) return rc;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, nslots * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, count * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
     s.timed = timing;
     s.busy = true; s.first = first; s.count = count;
@@ -334,7 +340,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     st->pack_ms += t2 - t1;
     s.trace_ms[0] = t1 - t0; s.trace_ms[1] = t2 - t1; s.trace_ms[2] = now_ms() - t2;
     st->h2d += s.in_bytes;
-    st->d2h += nslots * sizeof(SlotResult);
+    st->d2h += count * sizeof(SlotResult);
     st->launches += s.nlaunch;
     return 0;
 }
@@ -347,22 +353,19 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
     s.busy = false;
     float ms = 0.f;
     if (s.timed) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
-    const Plan& P = s.plan;
-    const size_t nslots = P.slots.size();
-    const size_t first = s.first;
+    const size_t first = s.first, count = s.count;
     const SlotResult* h_out = s.h_out;
     int bad = 0;
     uint64_t cell_sum = 0;
-    for (size_t k = 0; k < nslots; ++k) {
-        const int64_t t = P.slot_task[k];
-        if (t < 0) continue;
-        const SlotResult& r = h_out[k];
-        if (r.status == STATUS_OVERFLOW) { overflow->push_back(first + (size_t)t); continue; }     // K1R ring too small: rerun on K2
+    // the kernels wrote every record at its task's index: a sequential pass
+    for (size_t t = 0; t < count; ++t) {
+        const SlotResult& r = h_out[t];
+        if (r.status == STATUS_OVERFLOW) { overflow->push_back(first + t); continue; }     // K1R ring too small: rerun on K2
         if (r.status != STATUS_OK) bad = 1;
         cell_sum += (uint32_t)r.cells;
-        bsw_result& o = out[first + (size_t)t];
+        bsw_result& o = out[first + t];
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
-        if (cells) cells[first + (size_t)t] = (uint32_t)r.cells;
+        if (cells) cells[first + t] = (uint32_t)r.cells;
     }
     st->tasks += s.count; st->cells += cell_sum; st->kernel_ms += ms;
     (void)overflow;
@@ -420,25 +423,15 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     if (nworkers < 1) nworkers = 1;
     for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
 
-    // Guided self-scheduling: a worker takes remaining/(guide*workers) tasks, at most `chunk` and at least chunk/4 --
-    // big chunks while there is plenty of work (few launches, well-filled GPU), small ones near the end so that the
-    // work still on the GPU after the last chunk is packed (the un-overlapped tail of the call) is short.
-    // Measured on 1 M x 150 bp: shrinking chunks cost more (launches, copies) than the shorter tail saves, so the default
-    // (min_div 1) is fixed-size chunks; BSW_GUIDE / BSW_MIN_DIV keep the experiment reachable.
-    static const size_t guide = getenv("BSW_GUIDE") ? (size_t)std::max(1, atoi(getenv("BSW_GUIDE"))) : 1;
-    static const size_t min_div = getenv("BSW_MIN_DIV") ? (size_t)std::max(1, atoi(getenv("BSW_MIN_DIV"))) : 1;
-    const size_t min_chunk = std::max<size_t>(32, chunk / min_div);
+    // Fixed-size chunks pulled from a shared cursor.  Measured alternatives on 1 M x 150 bp, all slower: chunks that
+    // shrink towards the end of the batch (shorter un-overlapped tail, but more launches and copies: 6.5 -> 7.0-9 ms)
+    // and a ramp-up of small first chunks (GPU starts earlier: 6.5 -> 6.9 ms).
     std::atomic<size_t> cursor(0);
     auto grab = [&](size_t* first, size_t* count) -> bool {
-        size_t cur = cursor.load(std::memory_order_relaxed);
-        for (;;) {
-            if (cur >= n) return false;
-            const size_t rem = n - cur;
-            size_t c = std::min(chunk, std::max(min_chunk, rem / (guide * nworkers)));
-            c = (c + 31) & ~(size_t)31;
-            if (c > rem || rem - c < min_chunk / 2) c = rem;
-            if (cursor.compare_exchange_weak(cur, cur + c, std::memory_order_relaxed)) { *first = cur; *count = c; return true; }
-        }
+        const size_t cur = cursor.fetch_add(chunk, std::memory_order_relaxed);
+        if (cur >= n) return false;
+        *first = cur; *count = std::min(chunk, n - cur);
+        return true;
     };
     std::atomic<int> first_err(0);
     std::mutex stat_mu;
@@ -1077,7 +1070,7 @@ int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t*
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     size_t nl = 0;
     { int rc = enqueue_gather(ctx, s);                  // the device half of the scheduler is part of every pass
-      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl, ctx->opt.k2_sub);
+      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl, ctx->opt.k2_sub, nullptr);
       if (rc) { cudaSetDevice(prev); return rc; }
       if (s.plan.n_k1_tiles) ++nl; }
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));

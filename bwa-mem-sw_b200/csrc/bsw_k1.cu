@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
         const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u + lane;
         SlotResult r;
         k1_task<VARIANT, GENERIC, SYM>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, (int)nqw, eh + lane, qs + lane, tg, r);
-        int4* o = reinterpret_cast<int4*>(A.out + slot);
+        int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
         o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
         o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
         my_cells = (uint32_t)r.cells;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(K1_NT) k1r_extend_kernel(const __grid_constant
         const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u + lane;
         SlotResult r;
         k1_task<1, GENERIC, SYM, K1R_RING>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, (int)nqw, eh + lane, qs, tg, r, false);
-        int4* o = reinterpret_cast<int4*>(A.out + slot);
+        int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
         o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
         o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
         my_cells = (uint32_t)r.cells;

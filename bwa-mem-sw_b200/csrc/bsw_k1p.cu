@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(K1P_NT) k1p_extend_kernel(const __grid_constan
         SlotResult ra, rb;
         k1p_pair<SYM>(A.p, spa, spb, (int)nqa, (int)nqb, eh + 2 * lane, qsa + lane, qsb + lane, tga, tgb, ra, rb);
         if (spa.qlen > 0) {
-            int4* o = reinterpret_cast<int4*>(A.out + slot_a);
+            int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot_a] : slot_a));
             o[0] = make_int4(ra.score, ra.qle, ra.tle, ra.gtle);
             o[1] = make_int4(ra.gscore, ra.max_off, ra.cells, ra.status);
             my_cells += (uint32_t)ra.cells;
         }
         if (spb.qlen > 0) {
-            int4* o = reinterpret_cast<int4*>(A.out + slot_b);
+            int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot_b] : slot_b));
             o[0] = make_int4(rb.score, rb.qle, rb.tle, rb.gtle);
             o[1] = make_int4(rb.gscore, rb.max_off, rb.cells, rb.status);
             my_cells += (uint32_t)rb.cells;

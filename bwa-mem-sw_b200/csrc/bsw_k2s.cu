@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(32) k2s_extend_kernel(const __grid_constant__ 
     }
 
     if (sl == 0 && has_task) {
-        int4* o = reinterpret_cast<int4*>(A.out + slot);
+        int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
         const unsigned long long cc = cells > 0x7fffffffull ? 0x7fffffffull : cells;
         o[0] = make_int4(max, max_j + 1, max_i + 1, max_ie + 1);                   // sx:1315-1375 (score,qle,tle,gtle)
         o[1] = make_int4(gscore, max_off, overflow ? 0 : (int)cc, overflow ? STATUS_OVERFLOW : STATUS_OK);

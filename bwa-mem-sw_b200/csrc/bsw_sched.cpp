@@ -59,53 +59,6 @@ int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, 
     return w;
 }
 
-// ---- packing: 16 bases per SSE2 op, validation fused ----
-// Packs `len` bases into dst (ceil(len/8) words, then zero-padded to a multiple of 4 words).  Returns the number of
-// words written (multiple of 4); *mx accumulates the bytewise maximum of the codes (validation: max <= 4, and max == 4
-// <=> the task holds an N), so the check costs one op per 16 bases.
-alignas(16) static const uint8_t k_tail_mask[32] = { 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
-                                                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-static inline __m128i nib16(__m128i x, __m128i lowbyte)
-{
-    // per 16-bit lane {b1,b0} -> b0 | b1<<4 in the low byte
-    return _mm_and_si128(_mm_or_si128(x, _mm_srli_epi16(x, 4)), lowbyte);
-}
-static inline int pack_seq16(const uint8_t* s, int len, uint32_t* dst, __m128i* mx)
-{
-    const __m128i lowbyte = _mm_set1_epi16(0x00ff);
-    __m128i m = *mx;
-    int k = 0, done = 0;
-    for (; done + 32 <= len; done += 32, k += 4) {
-        const __m128i x0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done));
-        const __m128i x1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done + 16));
-        m = _mm_max_epu8(m, _mm_max_epu8(x0, x1));
-        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(nib16(x0, lowbyte), nib16(x1, lowbyte)));
-    }
-    // the last 1..31 bases: two 16-byte loads masked to the sequence.  Reading past the end is harmless as long as the
-    // load stays inside the page of a byte we own; next to a page end the bytes go through a bounce buffer instead.
-    const int rem = len - done;
-    if (rem > 0) {
-        __m128i x0, x1;
-        if (((uintptr_t)(s + done) & 4095u) <= 4096u - 32u) {
-            x0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done));
-            x1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + done + 16));
-        } else {
-            alignas(16) uint8_t buf[32];
-            for (int j = 0; j < 32; ++j) buf[j] = j < rem ? s[done + j] : 0;
-            x0 = _mm_load_si128(reinterpret_cast<const __m128i*>(buf));
-            x1 = _mm_load_si128(reinterpret_cast<const __m128i*>(buf + 16));
-        }
-        const int r0 = rem < 16 ? rem : 16, r1 = rem - r0;
-        x0 = _mm_and_si128(x0, _mm_loadu_si128(reinterpret_cast<const __m128i*>(k_tail_mask + 16 - r0)));
-        x1 = _mm_and_si128(x1, _mm_loadu_si128(reinterpret_cast<const __m128i*>(k_tail_mask + 16 - r1)));
-        m = _mm_max_epu8(m, _mm_max_epu8(x0, x1));
-        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + k), _mm_packus_epi16(nib16(x0, lowbyte), nib16(x1, lowbyte)));
-        k += 4;
-    }
-    *mx = m;
-    return k;
-}
-
 size_t source_arena_bound(const ExtTask* tasks, size_t n)
 {
     size_t words = 0;
@@ -119,47 +72,11 @@ size_t source_arena_bound(const ExtTask* tasks, size_t n)
 int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg)
 {
-    const int k1cap = K1_QLEN_CAP;
-    size_t w = 0;                                       // next free word (multiple of 4)
-    for (size_t i = 0; i < n; ++i) {
-        const ExtTask& t = tasks[i];
-        if (t.qlen == 0 && t.w == -2) { cls[i] = 0x80; src[i] = SlotSrc{ 0, 0 }; continue; }     // absent flank of a seed task
-        int e = 0;
-        if (!t.q || !t.t || t.qlen < 1 || t.tlen < 1 || t.h0 < 1 || t.w < 0) e = BSW_EINVAL;
-        else if ((int64_t)t.h0 + (int64_t)t.qlen * max_mat > SCORE_CAP || t.qlen > K2_QLEN_CAP || t.tlen > 500000) e = BSW_ERANGE;
-        uint8_t c = 0;
-        if (!e) {
-            __m128i mx = _mm_setzero_si128();
-            src[i].qoff16 = (uint32_t)(w >> 2);
-            w += (size_t)pack_seq16(t.q, t.qlen, arena + w, &mx);
-            src[i].toff16 = (uint32_t)(w >> 2);
-            w += (size_t)pack_seq16(t.t, t.tlen, arena + w, &mx);
-            const __m128i four = _mm_set1_epi8(4);
-            if (_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_max_epu8(mx, four), four)) != 0xffff) e = BSW_EINVAL;     // some code > 4
-            if (_mm_movemask_epi8(_mm_cmpeq_epi8(mx, four)) || !opt.fast_matrix) c |= 1;                       // some code == 4
-            bool longtask = opt.force_kernel == 2 || (opt.force_kernel == 0 && t.qlen >= opt.k2_min_qlen) || t.qlen > k1cap;
-            if (opt.variant == 2) {               // K2 implements the V1 recurrence only
-                longtask = false;
-                if (!e && (t.qlen > k1cap || opt.force_kernel == 2)) e = BSW_ERANGE;
-            }
-            if (longtask) c |= 2;
-            // K1R needs the first row (min(qlen, w+1) columns + end slot) inside the ring
-            if (longtask && opt.ring && opt.variant == 1 && opt.force_kernel != 2 && std::min(t.qlen, t.w + 1) + 2 <= K1R_RING) c |= 4;
-        }
-        cls[i] = c;
-        if (e) {
-            if (bad_task) *bad_task = i;
-            if (msg)
-                *msg = "task " + std::to_string(i) + ": qlen=" + std::to_string(t.qlen) + " tlen=" + std::to_string(t.tlen) +
-                       " h0=" + std::to_string(t.h0) + " w=" + std::to_string(t.w) +
-                       (e == BSW_ERANGE ? " outside the numeric envelope (16-bit row state / length caps / V2 long task)"
-                                        : " invalid (null pointer, length < 1, h0 < 1 or base code > 4)");
-            return e;
-        }
-    }
-    for (int k = 0; k < 8; ++k) arena[w + (size_t)k] = 0;     // slack: the gather may read one 16-byte unit past a sequence
-    *words_used = w + 8;
-    return 0;
+    // bsw_pack.cpp is compiled twice; the AVX-512 build packs 64 bases per step with masked loads (no tail branches)
+    static const bool wide = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                             __builtin_cpu_supports("bmi2") && !getenv("BSW_NO_AVX512");
+    return wide ? pack_tasks_avx512(tasks, n, max_mat, opt, cls, src, arena, words_used, bad_task, msg)
+                : pack_tasks_sse2(tasks, n, max_mat, opt, cls, src, arena, words_used, bad_task, msg);
 }
 
 // order[] = task indices by ascending 32-bit key (stable LSD radix).  The digit width follows the chunk size: three

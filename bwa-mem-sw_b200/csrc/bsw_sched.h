@@ -74,6 +74,11 @@ size_t source_arena_bound(const ExtTask* tasks, size_t n);
 // Returns 0 or a negative BSW_E* code; on error *bad_task is the first offending task and msg explains.
 int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
+// the two builds of bsw_pack.cpp behind pack_tasks (run-time dispatch on the CPU's ISA)
+int pack_tasks_sse2(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
+                    uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
+int pack_tasks_avx512(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
+                      uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
 
 // Level-2 plan: tasks[2*s] / tasks[2*s+1] are the left / right flank of seed s (qlen == 0: absent, cls 0x80).  Seeds are
 // sorted by their longer flank and cut into pairs of K1 tiles (left flanks, right flanks), 32 seeds per pair.
