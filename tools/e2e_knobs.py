@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     t = B.synth_tasks(sys.argv[2], n)
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     out = np.zeros(n, dtype=B.RESULT_DTYPE)
-    tag = " ".join("%s=%s" % (k, os.environ.get(k)) for k in ("CUDA_DEVICE_MAX_CONNECTIONS", "BSW_GUIDE", "BSW_MIN_DIV"))
+    tag = " ".join("%s=%s" % (k, os.environ.get(k)) for k in ("CUDA_DEVICE_MAX_CONNECTIONS", "BSW_BUCKET_PCT", "BSW_SIDE_STREAMS"))
     for slots in (2, 4):
         for chunk in (16384, 32768):
             ctx.set_option("slots", slots); ctx.set_option("chunk_tasks", chunk)
@@ -23,6 +23,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             print("%s slots %d chunk %6d: min %.2f median %.2f ms" % (tag, slots, chunk, ts[0], ts[len(ts) // 2]), flush=True)
 else:
     wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2_150bp"
-    for conn, guide, mind in itertools.product(("8", "32"), ("1", "2", "4"), ("1", "4", "8")):
-        env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS=conn, BSW_GUIDE=guide, BSW_MIN_DIV=mind)
+    for conn, pct, side in itertools.product(("8", "32"), ("130", "200", "100000"), ("1", "3")):
+        env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS=conn, BSW_BUCKET_PCT=pct, BSW_SIDE_STREAMS=side)
         subprocess.run([sys.executable, os.path.abspath(__file__), "child", wl], env=env)
