@@ -338,3 +338,90 @@ extern "C" int bsw_emu_chain2aln(const bsw_params2* P2, int variant, const bsw_s
     }
     return BSW_OK;
 }
+
+// ---- host-logic self checks (tests/test_host_logic.py) ----
+#include <sys/mman.h>
+#include <unistd.h>
+// Packs random sequences with both builds of bsw_pack.cpp and compares them with a scalar packer.  Every sequence ends
+// flush against an inaccessible page, so a packer that reads past a sequence faults instead of passing.
+// Returns 0, or 1000+i when task i differs, or a negative setup error.  *used_avx512 reports whether that build ran.
+extern "C" int bsw_emu_pack_check(uint64_t seed, int ntasks, int max_len, int* used_avx512)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t span = (((size_t)max_len + page - 1) / page + 1) * page;           // data pages + 1 guard page
+    const bool wide = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("bmi2");
+    if (used_avx512) *used_avx512 = wide ? 1 : 0;
+    uint8_t* base = static_cast<uint8_t*>(mmap(nullptr, 2 * span * (size_t)ntasks, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (base == MAP_FAILED) return -1;
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    std::vector<ExtTask> tasks((size_t)ntasks);
+    for (int i = 0; i < ntasks; ++i) {
+        for (int side = 0; side < 2; ++side) {
+            uint8_t* blk = base + (size_t)(2 * i + side) * span;
+            if (mprotect(blk + span - page, page, PROT_NONE)) return -2;
+            const int len = 1 + (int)(rnd() % (uint64_t)max_len);
+            uint8_t* sq = blk + span - page - (size_t)len;                          // last base = last readable byte
+            const bool with_n = rnd() % 7 == 0;
+            for (int k = 0; k < len; ++k) sq[k] = (uint8_t)((with_n && rnd() % 11 == 0) ? 4 : rnd() & 3);
+            if (side == 0) { tasks[(size_t)i].q = sq; tasks[(size_t)i].qlen = len; } else { tasks[(size_t)i].t = sq; tasks[(size_t)i].tlen = len; }
+        }
+        tasks[(size_t)i].h0 = 1 + (int)(rnd() % 50); tasks[(size_t)i].w = (int)(rnd() % 100);
+    }
+    SchedOptions opt; opt.fast_matrix = true;
+    const size_t bound = source_arena_bound(tasks.data(), (size_t)ntasks);
+    int rc = 0;
+    for (int isa = 0; isa < (wide ? 2 : 1) && !rc; ++isa) {
+        std::vector<uint32_t> arena(bound, 0xdeadbeefu);
+        std::vector<uint8_t> cls((size_t)ntasks); std::vector<SlotSrc> src((size_t)ntasks);
+        size_t used = 0, bad = 0; std::string msg;
+        const int e = (isa ? pack_tasks_avx512 : pack_tasks_sse2)(tasks.data(), (size_t)ntasks, 1, opt, cls.data(), src.data(), arena.data(), &used, &bad, &msg);
+        if (e || used > bound) { rc = -3; break; }
+        for (int i = 0; i < ntasks && !rc; ++i) {
+            const ExtTask& t = tasks[(size_t)i];
+            bool has_n = false;
+            for (int side = 0; side < 2 && !rc; ++side) {
+                const uint8_t* sq = side ? t.t : t.q; const int len = side ? t.tlen : t.qlen;
+                const uint32_t* w = arena.data() + (size_t)(side ? src[(size_t)i].toff16 : src[(size_t)i].qoff16) * 4;
+                const int words = ((len + 31) / 32) * 4;
+                for (int k = 0; k < words * 8; ++k) {
+                    const uint32_t got = (w[k >> 3] >> (4 * (k & 7))) & 15u, want = k < len ? sq[k] : 0u;
+                    if (got != want) { rc = 1000 + i; break; }
+                    if (want == 4) has_n = true;
+                }
+            }
+            if (!rc && ((cls[(size_t)i] & 1) != (has_n ? 1 : 0))) rc = 1000 + i;
+        }
+        // a bad code anywhere must be rejected with the task's index
+        if (!rc) {
+            const int victim = (int)(rnd() % (uint64_t)ntasks);
+            uint8_t* sq = const_cast<uint8_t*>(tasks[(size_t)victim].t);
+            const int pos = (int)(rnd() % (uint64_t)tasks[(size_t)victim].tlen);
+            const uint8_t keep = sq[pos]; sq[pos] = 5 + (uint8_t)(rnd() % 200);
+            const int e2 = (isa ? pack_tasks_avx512 : pack_tasks_sse2)(tasks.data(), (size_t)ntasks, 1, opt, cls.data(), src.data(), arena.data(), &used, &bad, &msg);
+            sq[pos] = keep;
+            if (e2 != BSW_EINVAL || bad != (size_t)victim) rc = -4;
+        }
+    }
+    munmap(base, 2 * span * (size_t)ntasks);
+    return rc;
+}
+
+// BandClamp (tabulated) against clamp_band (the two divisions) over a grid of lengths, bands and penalties.
+extern "C" int bsw_emu_band_clamp_check()
+{
+    int8_t mat[25];
+    for (int a = 1; a <= 3; ++a)
+        for (int oi = 0; oi <= 12; oi += 3)
+            for (int ei = 1; ei <= 4; ++ei)
+                for (int od = 0; od <= 12; od += 4)
+                    for (int ed = 1; ed <= 3; ++ed)
+                        for (int eb = 0; eb <= 10; eb += 5) {
+                            for (int k = 0; k < 25; ++k) mat[k] = (int8_t)((k % 6 == 0 && k < 24) ? a : -4);
+                            const BandClamp c(mat, eb, oi, ei, od, ed);
+                            for (int q = 1; q <= 1400; q += (q < 300 ? 1 : 37))
+                                for (int w = 0; w <= 400; w += 7)
+                                    if (c(q, w) != clamp_band(mat, q, w, eb, oi, ei, od, ed)) return 1;
+                        }
+    return 0;
+}
