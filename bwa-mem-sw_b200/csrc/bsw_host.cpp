@@ -99,7 +99,7 @@ struct bsw_ctx {
     int slots_per_worker = 2;      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
-    bool kernel_timing = true;     // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms)
+    bool kernel_timing = false;    // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms); two more driver calls per chunk
     std::mutex mu;                 // serialises batch calls on this context
     std::mutex err_mu;
     std::string last_error;
@@ -240,17 +240,19 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
     // A plan has one launch per class and occupancy bucket; issued on one stream each would wait for the previous
     // launch's last CTA (0.2-0.4 ms of tile latency each, measured 1.0 ms -> 0.38 ms for a 32 k task chunk).  Spread
     // them over the slot's four streams (fork after the gather, join before the D2H).
-    const bool spread = P.launches.size() > 1;
     static const int nside = getenv("BSW_SIDE_STREAMS") ? std::max(0, std::min(5, atoi(getenv("BSW_SIDE_STREAMS")))) : 3;
+    // only as many side streams as there are extra launches (every fork/join is four driver calls)
+    const int nuse = (int)std::min<size_t>((size_t)nside, P.launches.size() > 0 ? P.launches.size() - 1 : 0);
+    const bool spread = nuse > 0;
     if (spread) {
         CUDA_TRY(ctx, cudaEventRecord(s.ev_fork, s.stream));
-        for (int k = 0; k < nside; ++k) CUDA_TRY(ctx, cudaStreamWaitEvent(s.side[k], s.ev_fork, 0));
+        for (int k = 0; k < nuse; ++k) CUDA_TRY(ctx, cudaStreamWaitEvent(s.side[k], s.ev_fork, 0));
     }
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
         a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
-        const size_t lane_ix = nl % (size_t)(nside + 1);
+        const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
                       : (L.kind == 3) ? k1p_launch(a, sym, st)
@@ -261,7 +263,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         ++nl;
     }
     if (spread) {
-        for (int k = 0; k < nside; ++k) {
+        for (int k = 0; k < nuse; ++k) {
             CUDA_TRY(ctx, cudaEventRecord(s.ev_join[k], s.side[k]));
             CUDA_TRY(ctx, cudaStreamWaitEvent(s.stream, s.ev_join[k], 0));
         }

@@ -248,7 +248,7 @@ static cudaError_t k2s_launch_t(const LaunchArgs& a, cudaStream_t st)
     const size_t smem = (size_t)K2S_HDR_BYTES + (size_t)TPW * k2s_task_words(rcap) * 4u + 16u;
     auto kern = k2s_extend_kernel<GENERIC, SW>;
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t err = ensure_max_smem(kern);
     if (err != cudaSuccess) return err;
     kern<<<(a.ntiles + TPW - 1) / TPW, 32, smem, st>>>(a);
     return cudaGetLastError();

@@ -2,6 +2,28 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "bsw_device.cuh"
+#include <atomic>
+
+namespace bsw {
+// Opt the kernel into the full 227 KB of dynamic shared memory, once per kernel instantiation and device.  Always the
+// same (maximal) value: launches come concurrently from several host threads, a per-launch value would race; and a
+// driver call per launch is what the host workers contend on (22 -> ~10 API calls per chunk with this and the
+// narrower stream fork).
+template <class Kernel>
+inline cudaError_t ensure_max_smem(Kernel kern)
+{
+    static std::atomic<unsigned> done{ 0u };                  // one bit per device id < 32
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned bit = 1u << (dev & 31);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+}  // namespace bsw
+
 
 namespace bsw {
 

@@ -53,9 +53,13 @@ int  bsw_init(bsw_ctx **ctx, const int *device_ids, int n_devices, int streams_p
 void bsw_destroy(bsw_ctx *ctx);
 const char *bsw_last_error(const bsw_ctx *ctx);          /* thread-unsafe convenience: last error text of this ctx */
 const char *bsw_version(void);
-/* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity);
+/* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity, default 16384);
+ * "slots" N (chunks one host worker keeps in flight, default 2);
  * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
- * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 1) */
+ * "k2_warps" {1,4} warps per K2 task; "fused_l2" {0,1} level 2 as one fused kernel (default 1);
+ * experimental kernels, off by default because they measured slower: "k1_pair", "ring", "k2_sub";
+ * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 0:
+ *                       the batch calls then leave kernel_ms at 0; bsw_resident_run always times its launches) */
 int  bsw_set_option(bsw_ctx *ctx, const char *key, int64_t value);
 int  bsw_num_devices(const bsw_ctx *ctx);
 

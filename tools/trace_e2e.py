@@ -3,8 +3,8 @@ import sys, os, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path
 import bsw_b200 as B
 import numpy as np
 ctx = B.Context()
-n = 1000000
-t = B.synth_tasks("cfg2_150bp", n)
+n = int(os.environ.get("N", "1000000"))
+t = B.synth_tasks(os.environ.get("WL", "cfg2_150bp"), n)
 p = B.make_params()
 flat = (t['qbuf'], t['qoff'], t['tbuf'], t['toff'], t['h0'], t['w'])
 if os.environ.get("CHUNK"): ctx.set_option("chunk_tasks", int(os.environ["CHUNK"]))
