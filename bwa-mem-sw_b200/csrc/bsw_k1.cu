@@ -110,7 +110,8 @@ static cudaError_t k1r_launch_t(const LaunchArgs& a, cudaStream_t st)
     if (!a.ntiles) return cudaSuccess;
     const size_t smem = (size_t)K1R_RING * K1_NT * 4u;
     auto kern = k1r_extend_kernel<GENERIC, SYM>;
-    cudaError_t err = ensure_max_smem(kern);
+    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
+    cudaError_t err = ensure_max_smem(kern, smem_set);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles, K1_NT, smem, st>>>(a);
     return cudaGetLastError();
@@ -136,7 +137,8 @@ static cudaError_t k1_launch_t(const LaunchArgs& a, cudaStream_t st)
     // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
     // value would race with another thread's launch of the same kernel
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t err = ensure_max_smem(kern);
+    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
+    cudaError_t err = ensure_max_smem(kern, smem_set);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles, K1_NT, smem, st>>>(a);
     return cudaGetLastError();

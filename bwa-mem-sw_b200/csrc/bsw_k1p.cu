@@ -98,7 +98,8 @@ static cudaError_t k1p_launch_t(const LaunchArgs& a, cudaStream_t st)
     const size_t smem = k1p_smem_bytes(a.qmax, a.nqw_max);
     auto kern = k1p_extend_kernel<SYM>;
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t err = ensure_max_smem(kern);
+    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
+    cudaError_t err = ensure_max_smem(kern, smem_set);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles / 2, K1P_NT, smem, st>>>(a);
     return cudaGetLastError();

@@ -321,7 +321,8 @@ static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
     // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
     // value would race with another thread's launch of the same kernel
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t err = ensure_max_smem(kern);
+    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
+    cudaError_t err = ensure_max_smem(kern, smem_set);
     if (err != cudaSuccess) return err;
     kern<<<a.ntiles, 32 * NW, smem, st>>>(a);
     return cudaGetLastError();

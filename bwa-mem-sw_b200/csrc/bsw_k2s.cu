@@ -248,7 +248,8 @@ static cudaError_t k2s_launch_t(const LaunchArgs& a, cudaStream_t st)
     const size_t smem = (size_t)K2S_HDR_BYTES + (size_t)TPW * k2s_task_words(rcap) * 4u + 16u;
     auto kern = k2s_extend_kernel<GENERIC, SW>;
     if (smem > 232448) return cudaErrorInvalidValue;
-    cudaError_t err = ensure_max_smem(kern);
+    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
+    cudaError_t err = ensure_max_smem(kern, smem_set);
     if (err != cudaSuccess) return err;
     kern<<<(a.ntiles + TPW - 1) / TPW, 32, smem, st>>>(a);
     return cudaGetLastError();

@@ -9,10 +9,10 @@ namespace bsw {
 // same (maximal) value: launches come concurrently from several host threads, a per-launch value would race; and a
 // driver call per launch is what the host workers contend on (22 -> ~10 API calls per chunk with this and the
 // narrower stream fork).
+// `done` is the calling launcher's own static (one per kernel instantiation): one bit per device id < 32.
 template <class Kernel>
-inline cudaError_t ensure_max_smem(Kernel kern)
+inline cudaError_t ensure_max_smem(Kernel kern, std::atomic<unsigned>& done)
 {
-    static std::atomic<unsigned> done{ 0u };                  // one bit per device id < 32
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
