@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 # libbsw.so's host pipeline drives ~100 streams: ask the driver for 32 hardware queues before any CUDA context exists
 # (the bsw_b200 package sets the same default on import; torch would otherwise create the context first)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# stdout carries exactly one JSON line: NCCL's version banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
