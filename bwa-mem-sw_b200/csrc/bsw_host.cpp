@@ -40,7 +40,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t side[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // extra streams: the bucket launches of one big plan overlap their tails
     cudaEvent_t ev_fork = nullptr, ev_join[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr, ev_in = nullptr, ev_out = nullptr;   // ev_in/ev_out: BSW_TRACE only
     // One pinned input block per chunk, mirrored on the device and moved with a single cudaMemcpyAsync:
     //   [ source arena (task-major packed sequences) | TileHdr[] | SlotParam[] | SlotSrc[] | u32 task-of-slot[] ]   (16-byte aligned parts)
     unsigned char* h_in = nullptr; size_t h_in_cap = 0;
@@ -99,6 +99,8 @@ struct bsw_ctx {
     int slots_per_worker = 2;      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
+    cudaEvent_t trace_ref = nullptr;   // BSW_TRACE: recorded at the start of a batch call, origin of the per-chunk GPU timeline
+    double trace_ref_host_ms = 0;      // host time (relative to the call start) at which trace_ref was recorded
     bool kernel_timing = false;    // record CUDA events around each chunk's kernels (bsw_stats.kernel_ms); two more driver calls per chunk
     std::mutex mu;                 // serialises batch calls on this context
     std::mutex err_mu;
@@ -168,6 +170,8 @@ int slot_init(bsw_ctx* ctx, Slot& s)
 {
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k0));
+    CUDA_TRY(ctx, cudaEventCreate(&s.ev_in));
+    CUDA_TRY(ctx, cudaEventCreate(&s.ev_out));
     CUDA_TRY(ctx, cudaEventCreate(&s.ev_k1));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
@@ -190,6 +194,8 @@ void slot_free(Slot& s)
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_cells) cudaFree(s.d_cells);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_out) cudaEventDestroy(s.ev_out);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_fork) cudaEventDestroy(s.ev_fork);
@@ -328,12 +334,14 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     const double t2 = now_ms();
 
     // per chunk: 1 H2D, 1 gather, the bucket launches, 1 D2H, 1 event (the per-task cells come back in the records)
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_in, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if ((rc = enqueue_gather(ctx, s))) return rc;
     if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub, s.d_oidx()))) return rc;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, count * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_out, s.stream));
     CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
     s.timed = timing;
     s.busy = true; s.first = first; s.count = count;
@@ -355,6 +363,12 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
     s.busy = false;
     float ms = 0.f;
     if (s.timed) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    if (s.timed && ctx->trace_ref) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, ctx->trace_ref, s.ev_in); cudaEventElapsedTime(&b, ctx->trace_ref, s.ev_k0);
+        cudaEventElapsedTime(&c, ctx->trace_ref, s.ev_k1); cudaEventElapsedTime(&d, ctx->trace_ref, s.ev_out);
+        fprintf(stderr, "gpu chunk %zu+%zu: h2d %.3f..%.3f kernels ..%.3f d2h ..%.3f ms\n", s.first, s.count, a, b, c, d);
+    }
     const size_t first = s.first, count = s.count;
     const SlotResult* h_out = s.h_out;
     int bad = 0;
@@ -489,6 +503,13 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     };
     int prev_dev = 0;
     cudaGetDevice(&prev_dev);
+    const bool gpu_trace = getenv("BSW_TRACE") != nullptr && ctx->kernel_timing;
+    if (gpu_trace) {
+        cudaSetDevice(ctx->devs[0].id);
+        if (!ctx->trace_ref) cudaEventCreate(&ctx->trace_ref);
+        cudaEventRecord(ctx->trace_ref, ctx->devs[0].aux.stream);
+        fprintf(stderr, "gpu timeline origin at host %.3f ms\n", now_ms() - w0);
+    }
     if (nworkers == 1) worker_main(0);
     else {
         std::vector<std::thread> th;

@@ -133,26 +133,44 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
     if (n == 0) return;
 
-    // sort key (32 bit, descending cost first): [class:3][qlen:13][tlen/4:10][h0/2:6]; the order is only a
-    // scheduling heuristic (any order gives the same results), so long lengths may saturate their field.
+    // Sort key (32 bit, descending cost first).  The order is only a scheduling heuristic (any order gives the same
+    // results), but it decides how much of a tile's time its lanes idle: the lanes advance row by row together, so a tile
+    // costs (rows of its longest lane) x (width of its widest live window).  The window of a row is about min(qlen, h0)
+    // wide (the non-zero run around the diagonal grows with the score budget): tlen * min(qlen, h0) predicts the cell
+    // count of a 150 bp task with correlation 0.99 (tools/tile_efficiency.py).
+    //   chunk plans (< 100 k tasks), K1 classes: [class:3][qlen/16:11][min(qlen,h0)/4:9][tlen/4:9] -- a coarse qlen
+    //       bucket (it sets the tile's shared memory, i.e. the occupancy bucket), then the window width, then the rows.
+    //       Lane efficiency of 16 k task chunks (row-lockstep model) against the key below: 150 bp reads 0.89 -> 0.96,
+    //       50-250 bp mix 0.67 -> 0.87; measured e2e on 1 M tasks 6.45 -> 5.85 ms and 11.9 -> 8.3 ms.
+    //   big plans and K2 classes: [class:3][qlen:13][tlen/4:10][h0/2:6] (K2: qlen/8) -- with thousands of tasks per exact
+    //       qlen the three-level sort is already 0.99 efficient, and it measured 5 % faster there than the width key
+    //       (1 107 vs 1 050 GCUPS on the resident 1 M x 150 bp plan).
     // classes: 0 K1 fast, 1 K1 matrix, 2 K1R fast, 3 K1R matrix, 4 K2 fast, 5 K2 matrix
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
     key.resize(n); order.resize(n); tmp.resize(n);
+    const bool width_key = n < 100000;
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& t = tasks[i];
         const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
-        const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 3, 8191) : (uint32_t)std::min(t.qlen, 8191);
-        const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
-        key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
+        if ((cls[i] & 2u) || !width_key) {
+            const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 3, 8191) : (uint32_t)std::min(t.qlen, 8191);
+            const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
+            key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
+        } else {
+            const uint32_t qb = (uint32_t)std::min(t.qlen >> 4, 2047);
+            const uint32_t wd = (uint32_t)std::min(std::min(t.qlen, t.h0) >> 2, 511), tl = (uint32_t)std::min(t.tlen >> 2, 511);
+            key[i] = (c << 29) | ((2047u - qb) << 18) | ((511u - wd) << 9) | (511u - tl);
+        }
     }
     radix_order(key.data(), n, order, tmp, hist);
 
     // new occupancy bucket (= new launch) when a tile would fit at >= 1.15x the CTAs/SM of the current bucket (big plans;
-    // measured best with the launches spread over four streams) or >= 2x (the chunks of the host pipeline: every extra
-    // launch and stream costs more there than the occupancy it buys -- e2e 8.0 -> 6.5 ms on 1 M x 150 bp)
+    // measured best with the launches spread over four streams), >= 1.3x (100-400 k tasks) or >= 2x (the chunks of the
+    // host pipeline: every extra launch and stream costs more there than the occupancy it buys -- e2e 8.0 -> 6.5 ms on
+    // 1 M x 150 bp)
     static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
-    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : 200);
+    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : (n >= 100000 ? 130 : 200));
     // tiles
     const size_t nslot_bound = n + (size_t)8 * TILE_LANES;
     plan->slots.reserve(nslot_bound); plan->slot_src.reserve(nslot_bound); plan->slot_task.reserve(nslot_bound);

@@ -9,6 +9,7 @@ p = B.make_params()
 flat = (t['qbuf'], t['qoff'], t['tbuf'], t['toff'], t['h0'], t['w'])
 if os.environ.get("CHUNK"): ctx.set_option("chunk_tasks", int(os.environ["CHUNK"]))
 if os.environ.get("SLOTS"): ctx.set_option("slots", int(os.environ["SLOTS"]))
+if os.environ.get("GPU_TIMELINE"): ctx.set_option("kernel_timing", 1)     # adds the per-chunk GPU timeline to the trace
 out = np.zeros(n, dtype=B.RESULT_DTYPE)
 for _ in range(4): ctx.sw_extend_batch(p, *flat, want_cells=False, out=out)
 os.environ["BSW_TRACE"] = "1"
