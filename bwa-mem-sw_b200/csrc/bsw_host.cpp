@@ -858,7 +858,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
             const bsw_seed_task& s = tasks[elig[first + k]];
             ExtTask& l = sl.tasks[2 * k]; ExtTask& rr = sl.tasks[2 * k + 1];
             l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
-            rr.q = s.q_right; rr.t = s.t_right; rr.qlen = s.qlen[1]; rr.tlen = s.qlen[1] ? s.tlen[1] : 0; rr.h0 = s.qlen[1] ? 1 : 0; rr.w = s.qlen[1] ? 0 : -2;
+            rr.q = s.q_right; rr.t = s.t_right; rr.qlen = s.qlen[1]; rr.tlen = s.qlen[1] ? s.tlen[1] : 0; rr.h0 = s.qlen[1] ? 1 : 0; rr.w = s.qlen[1] ? (s.qlen[0] ? std::max(s.h0, 0) + s.qlen[0] : std::max(std::max(s.init_score, s.h0), 0)) : -2;   // present flank: score-budget hint for the seed plan's sort key
         }
         const size_t src_bound = source_arena_bound(sl.tasks.data(), 2 * cnt) * 4;
         const size_t max_slots = 2 * (cnt + 2 * TILE_LANES), max_tiles = max_slots / TILE_LANES + 4;

@@ -286,12 +286,21 @@ void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* sr
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
     key.resize(n); order.resize(n); tmp.resize(n);
+    // Sort key: the lanes of a K3 tile run the left extensions together, then the right ones, so a tile costs (longest
+    // left flank) + (longest right flank) and both must be alike across its lanes.  [matrix class:1][longer flank/16:7
+    // (shared memory of the tile pair)][estimated left cells/512:12][estimated right cells/128:12], cells estimated as
+    // tlen * min(qlen, score budget) like build_plan does (the right flank starts from about h0 + left qlen, which the
+    // caller passes in the right task's otherwise unused w).  Modelled
+    // lane efficiency of 8 k seed chunks (tools/seed_tile_efficiency.py): 0.52 with the former (longer flank, mean flank,
+    // h0) key -> 0.84.
     for (size_t i = 0; i < n; ++i) {
         const ExtTask& l = tasks[2 * i]; const ExtTask& r = tasks[2 * i + 1];
         const uint32_t g = ((cls[2 * i] | cls[2 * i + 1]) & 1u);
-        const uint32_t ql = (uint32_t)std::min(std::max(l.qlen, r.qlen), 16383);
-        const uint32_t qs = (uint32_t)std::min((l.qlen + r.qlen) >> 1, 1023), h = (uint32_t)std::min(l.h0 >> 1, 63);
-        key[i] = (g << 30) | ((16383u - ql) << 16) | ((1023u - qs) << 6) | (63u - h);
+        const uint32_t qb = (uint32_t)std::min(std::max(l.qlen, r.qlen) >> 4, 127);
+        const int64_t el = l.qlen > 0 ? (int64_t)l.tlen * std::min(l.qlen, l.h0) : 0;
+        const int64_t er = r.qlen > 0 ? (int64_t)r.tlen * std::min(r.qlen, std::max(r.w, 1)) : 0;     // r.w: budget hint set by the caller
+        const uint32_t bl = (uint32_t)std::min<int64_t>(el >> 9, 4095), br = (uint32_t)std::min<int64_t>(er >> 7, 4095);
+        key[i] = (g << 31) | ((127u - qb) << 24) | ((4095u - bl) << 12) | (4095u - br);
     }
     radix_order(key.data(), n, order, tmp, hist);
 
@@ -302,9 +311,9 @@ void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* sr
     };
     size_t i = 0;
     while (i < n) {
-        const uint32_t g = key[order[i]] >> 30;
+        const uint32_t g = key[order[i]] >> 31;
         size_t cend = i;
-        while (cend < n && (key[order[cend]] >> 30) == g) ++cend;
+        while (cend < n && (key[order[cend]] >> 31) == g) ++cend;
         Launch L{};
         L.kind = 5; L.generic = (int)g; L.tile0 = (uint32_t)plan->tiles.size();
         int occ0 = 0;

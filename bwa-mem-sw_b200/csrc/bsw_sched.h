@@ -80,7 +80,9 @@ int pack_tasks_sse2(const ExtTask* tasks, size_t n, int max_mat, const SchedOpti
 int pack_tasks_avx512(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                       uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
 
-// Level-2 plan: tasks[2*s] / tasks[2*s+1] are the left / right flank of seed s (qlen == 0: absent, cls 0x80).  Seeds are
+// Level-2 plan: tasks[2*s] / tasks[2*s+1] are the left / right flank of seed s (qlen == 0: absent, cls 0x80).  The band
+// of a seed task is decided on the device, so ExtTask.w is free: a present right flank carries its score-budget hint
+// there (about h0 + left qlen), which only feeds the sort key.  Seeds are
 // sorted by their longer flank and cut into pairs of K1 tiles (left flanks, right flanks), 32 seeds per pair.
 void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t nseeds, const SchedOptions& opt, Plan* plan);
 

@@ -299,7 +299,7 @@ extern "C" int bsw_emu_chain2aln(const bsw_params2* P2, int variant, const bsw_s
         const bsw_seed_task& s = tasks[k];
         ExtTask& l = v[2 * k]; ExtTask& r = v[2 * k + 1];
         l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
-        r.q = s.q_right; r.t = s.t_right; r.qlen = s.qlen[1]; r.tlen = s.qlen[1] ? s.tlen[1] : 0; r.h0 = s.qlen[1] ? 1 : 0; r.w = s.qlen[1] ? 0 : -2;
+        r.q = s.q_right; r.t = s.t_right; r.qlen = s.qlen[1]; r.tlen = s.qlen[1] ? s.tlen[1] : 0; r.h0 = s.qlen[1] ? 1 : 0; r.w = s.qlen[1] ? (s.qlen[0] ? std::max(s.h0, 0) + s.qlen[0] : std::max(std::max(s.init_score, s.h0), 0)) : -2;   // present flank: score-budget hint for the seed plan's sort key
     }
     std::vector<uint8_t> cls(2 * n);
     std::vector<SlotSrc> ssrc(2 * n);
