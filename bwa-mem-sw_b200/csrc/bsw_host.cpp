@@ -67,6 +67,7 @@ struct Slot {
     std::vector<ExtTask> tasks;
     std::vector<uint8_t> cls;
     std::vector<SlotSrc> src;
+    std::vector<size_t> seed_idx;    // level 2: the caller's seed index of every seed of the chunk in flight
 };
 
 // One host worker thread = one pipeline: it owns two staging slots (streams) on one device and alternates between
@@ -801,15 +802,18 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
                            const bsw_seed_clamp* clamps, bsw_aln_record* out, std::vector<size_t>* leftover)
 {
     std::lock_guard<std::mutex> lock(ctx->mu);
+    const double call0 = now_ms();
     DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
     int rc = make_dev_params(ctx, &P->p, &dp, &sym, &fast_ok, &max_mat);
     if (rc) return rc;
     SchedOptions opt = ctx->opt;
     opt.fast_matrix = fast_ok; opt.force_kernel = 1;
-    // eligibility / validation
-    std::vector<size_t> elig;
-    elig.reserve(n);
-    for (size_t i = 0; i < n; ++i) {
+    if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
+    // Validation and eligibility are checked by the workers, chunk by chunk (a serial scan of 1 M seed records cost
+    // 8 ms before the first chunk was even packed): a chunk is a range of the caller's seed array, its eligible seeds
+    // go through K3, the others are collected in `leftover` for the host-orchestrated path.
+    std::mutex left_mu;
+    auto check_seed = [&](size_t i, bool* eligible) -> int {
         const bsw_seed_task& s = tasks[i];
         const int ql = s.qlen[0], qr = s.qlen[1];
         if (ql < 0 || qr < 0 || (ql > 0 && (s.tlen[0] < 1 || s.h0 < 1 || !s.q_left || !s.t_left)) ||
@@ -819,16 +823,14 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         }
         const int64_t hmax = (int64_t)std::max(s.h0, s.init_score) + (int64_t)(ql + qr) * max_mat;
         if (hmax > SCORE_CAP) { set_error(ctx, "seed task " + std::to_string(i) + ": score bound exceeds the 16-bit row state"); return BSW_ERANGE; }
-        if (ql > K1_QLEN_CAP || qr > K1_QLEN_CAP || s.tlen[0] > 500000 || s.tlen[1] > 500000) leftover->push_back(i);
-        else elig.push_back(i);
-    }
-    if (elig.empty()) return BSW_OK;
-    if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
+        *eligible = !(ql > K1_QLEN_CAP || qr > K1_QLEN_CAP || s.tlen[0] > 500000 || s.tlen[1] > 500000);
+        return 0;
+    };
 
     // the same worker-pipeline structure as run_extensions: chunks of seeds pulled from a shared counter, every worker
     // packs / plans / submits on its own two stream slots
     const size_t chunk = 8192;           // measured on 200 k seeds: 4096 -> 9.1 ms, 8192 -> 6.9 ms, 16384 -> 7.2 ms
-    const size_t nchunks = (elig.size() + chunk - 1) / chunk;
+    const size_t nchunks = (n + chunk - 1) / chunk;
     const size_t ndev = ctx->devs.size();
     size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
     if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
@@ -836,7 +838,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
     std::atomic<size_t> next(0);
     std::atomic<int> first_err(0);
-    std::atomic<uint64_t> launches(0), h2d(0), d2h(0);
+    std::atomic<uint64_t> launches(0), h2d(0), d2h(0), fused_seeds(0);
 
     auto collect = [&](Slot& sl) -> int {
         if (!sl.busy) return 0;
@@ -847,15 +849,27 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         for (size_t q = 0; q < nlanes; ++q) {
             const int64_t sidx = sl.plan.lane_seed[q];
             if (sidx < 0) continue;
-            out[elig[sl.first + (size_t)sidx]] = recs[q];
+            out[sl.seed_idx[(size_t)sidx]] = recs[q];
         }
         return 0;
     };
-    auto submit = [&](Slot& sl, size_t first, size_t cnt) -> int {
+    auto submit = [&](Slot& sl, size_t first, size_t range) -> int {
         int r = 0;
+        sl.seed_idx.clear();
+        {
+            std::vector<size_t> left;
+            for (size_t i = first; i < first + range; ++i) {
+                bool ok = false;
+                if ((r = check_seed(i, &ok))) return r;
+                if (ok) sl.seed_idx.push_back(i); else left.push_back(i);
+            }
+            if (!left.empty()) { std::lock_guard<std::mutex> g(left_mu); leftover->insert(leftover->end(), left.begin(), left.end()); }
+        }
+        const size_t cnt = sl.seed_idx.size();
+        if (cnt == 0) return 0;
         sl.tasks.resize(2 * cnt); sl.cls.resize(2 * cnt); sl.src.resize(2 * cnt);
         for (size_t k = 0; k < cnt; ++k) {
-            const bsw_seed_task& s = tasks[elig[first + k]];
+            const bsw_seed_task& s = tasks[sl.seed_idx[k]];
             ExtTask& l = sl.tasks[2 * k]; ExtTask& rr = sl.tasks[2 * k + 1];
             l.q = s.q_left; l.t = s.t_left; l.qlen = s.qlen[0]; l.tlen = s.qlen[0] ? s.tlen[0] : 0; l.h0 = s.qlen[0] ? s.h0 : 0; l.w = s.qlen[0] ? 0 : -2;
             rr.q = s.q_right; rr.t = s.t_right; rr.qlen = s.qlen[1]; rr.tlen = s.qlen[1] ? s.tlen[1] : 0; rr.h0 = s.qlen[1] ? 1 : 0; rr.w = s.qlen[1] ? (s.qlen[0] ? std::max(s.h0, 0) + s.qlen[0] : std::max(std::max(s.init_score, s.h0), 0)) : -2;   // present flank: score-budget hint for the seed plan's sort key
@@ -869,7 +883,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         r = pack_tasks(sl.tasks.data(), 2 * cnt, max_mat, opt, sl.cls.data(), sl.src.data(), reinterpret_cast<uint32_t*>(sl.h_in),
                        &sl.src_words, &bad, &msg);
         if (r) {
-            set_error(ctx, "seed task " + std::to_string(elig[first + bad / 2]) + (bad & 1 ? " (right flank)" : " (left flank)") +
+            set_error(ctx, "seed task " + std::to_string(sl.seed_idx[bad / 2]) + (bad & 1 ? " (right flank)" : " (left flank)") +
                                ": invalid base code or length");
             return r;
         }
@@ -894,7 +908,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
             const int64_t sidx = PL.lane_seed[q];
             SeedParam& d = sp[q];
             if (sidx < 0) { d = SeedParam{ 0, 0, -1, 0, { -1, -1 }, { -1, -1 } }; continue; }
-            const size_t gi = elig[first + (size_t)sidx];
+            const size_t gi = sl.seed_idx[(size_t)sidx];
             const bsw_seed_task& s = tasks[gi];
             d.init_score = s.init_score; d.qbeg = s.qbeg; d.h0 = s.h0 > 0 ? s.h0 : 0; d.id = s.id;
             for (int side = 0; side < 2; ++side) {
@@ -919,7 +933,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         CUDA_TRY(ctx, cudaMemcpyAsync(sl.h_out, sl.d_out, nlanes * sizeof(SlotResult), cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(ctx, cudaEventRecord(sl.ev_done, sl.stream));
         sl.busy = true; sl.first = first; sl.count = cnt;
-        launches += nl; h2d += sl.in_bytes; d2h += nlanes * sizeof(SlotResult);
+        launches += nl; h2d += sl.in_bytes; d2h += nlanes * sizeof(SlotResult); fused_seeds += cnt;
         return 0;
     };
     auto worker_main = [&](size_t k) {
@@ -942,15 +956,15 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
             if ((r = collect(sl))) break;
             const size_t first = c * chunk;
             const double t1 = now_ms();
-            r = submit(sl, first, std::min(chunk, elig.size() - first));
-            if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu chunk %zu collect %.2f submit %.2f ms\n", k, c, t1 - t0, now_ms() - t1);
+            r = submit(sl, first, std::min(chunk, n - first));
+            if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu chunk %zu at %.2f: collect %.2f submit %.2f ms\n", k, c, t0 - call0, t1 - t0, now_ms() - t1);
         }
         const double t2 = now_ms();
         for (Slot& sl : W.slots) {
             if (r) { if (sl.stream) cudaStreamSynchronize(sl.stream); sl.busy = false; }
             else r = collect(sl);
         }
-        if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu drain %.2f ms\n", k, now_ms() - t2);
+        if (getenv("BSW_TRACE")) fprintf(stderr, "l2 w%zu drain at %.2f: %.2f ms\n", k, t2 - call0, now_ms() - t2);
         if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
     };
     int prev_dev = 0;
@@ -966,7 +980,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     {
         std::lock_guard<std::mutex> g(ctx->err_mu);
         ctx->stats.kernel_launches += launches.load(); ctx->stats.h2d_bytes += h2d.load(); ctx->stats.d2h_bytes += d2h.load();
-        ctx->stats.tasks += elig.size();
+        ctx->stats.tasks += fused_seeds.load();
     }
     return first_err.load();
 }
@@ -982,6 +996,7 @@ int bsw_chain2aln_impl(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* 
     std::vector<size_t> leftover;
     int rc = chain2aln_fused(ctx, P, tasks, n, clamps, out, &leftover);
     if (rc || leftover.empty()) return rc;
+    std::sort(leftover.begin(), leftover.end());          // the workers append in completion order
     // flanks longer than a K1 tile: host-orchestrated passes (K2 does the long extensions)
     std::vector<bsw_seed_task> lt(leftover.size());
     std::vector<bsw_seed_clamp> lc(clamps ? leftover.size() : 0);
