@@ -295,6 +295,47 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                 x = funnel_r(qs[qi * K1_S], qs[(qi + 1) * K1_S], (j & 7) * 4);
             }
             if (RING) ehp = BSW_EHA(j);
+            if (VARIANT == 1 && ONEHOT && !RING && nv >= 16) {
+                // two chunks under one head: one funnel shift yields the match bits of 16 columns, the 16 row-buffer
+                // loads are issued together, and the zero test, the loop bookkeeping and the branches are paid once
+                const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
+                const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
+                const uint32_t v0 = ehp[8 * K1_S], v1 = ehp[9 * K1_S], v2 = ehp[10 * K1_S], v3 = ehp[11 * K1_S];
+                const uint32_t v4 = ehp[12 * K1_S], v5 = ehp[13 * K1_S], v6 = ehp[14 * K1_S], v7 = ehp[15 * K1_S];
+                uint32_t zm = min3_u16x2(w0, w1, w2);
+                zm = min3_u16x2(zm, w3, w4);
+                zm = min3_u16x2(zm, w5, w6);
+                zm = min3_u16x2(zm, w7, v0);
+                zm = min3_u16x2(zm, v1, v2);
+                zm = min3_u16x2(zm, v3, v4);
+                zm = min3_u16x2(zm, v5, v6);
+                zm = min3_u16x2(zm, v7, v7);
+                if (zm >= 0x10000u) {                        // no zero H in the 16 columns
+                    int ckey = K1_KEY_NONE;
+                    BSW_K1_FAST(0, w0, x, true)
+                    BSW_K1_FAST(1, w1, x, true)
+                    BSW_K1_FAST(2, w2, x, true)
+                    BSW_K1_FAST(3, w3, x, true)
+                    BSW_K1_FAST(4, w4, x, true)
+                    BSW_K1_FAST(5, w5, x, true)
+                    BSW_K1_FAST(6, w6, x, true)
+                    BSW_K1_FAST(7, w7, x, true)
+                    mkey = imax(mkey, ckey + j);
+                    ehp += 8 * K1_S;
+                    const uint32_t x2 = x >> 8;
+                    BSW_K1_FAST(0, v0, x2, true)
+                    BSW_K1_FAST(1, v1, x2, true)
+                    BSW_K1_FAST(2, v2, x2, true)
+                    BSW_K1_FAST(3, v3, x2, true)
+                    BSW_K1_FAST(4, v4, x2, true)
+                    BSW_K1_FAST(5, v5, x2, true)
+                    BSW_K1_FAST(6, v6, x2, true)
+                    BSW_K1_FAST(7, v7, x2, true)
+                    mkey = imax(mkey, ckey + j + 8);
+                    j += 16; ehp += 8 * K1_S;
+                    continue;
+                }
+            }
             if (VARIANT == 1 && (!RING || (j & (RING - 1)) <= RING - 8)) {      // ring: a chunk that wraps goes cell by cell
                 const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
                 const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
@@ -316,6 +357,20 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                         mkey = imax(mkey, ckey + j);
                         j += 8; ehp += 8 * K1_S;
                         continue;
+                    }
+                } else if (nv <= 4) {
+                    // partial last chunk of at most four cells: half the work of the general one below
+                    const uint32_t ones = 0xffffffffu;
+                    uint32_t zm = min3_u16x2(w0, nv > 1 ? w1 : ones, nv > 2 ? w2 : ones);
+                    zm = min3_u16x2(zm, nv > 3 ? w3 : ones, ones);
+                    if (zm >= 0x10000u) {
+                        BSW_K1_FAST(0, w0, x, true)
+                        BSW_K1_FAST(1, w1, x, nv > 1)
+                        BSW_K1_FAST(2, w2, x, nv > 2)
+                        BSW_K1_FAST(3, w3, x, nv > 3)
+                        mkey = imax(mkey, ckey + j);
+                        j += nv; ehp += nv * K1_S;
+                        break;
                     }
                 } else {
                     // partial last chunk: the same code with the cells at or past lim made inert
