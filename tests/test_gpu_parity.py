@@ -184,6 +184,33 @@ def test_level2_proc_element(B, O, ctx, w, zdrop):
         assert (want["w"] == 2 * w).any()          # the retry path ran
 
 
+def test_level2_many_chunks_and_errors_found_by_the_workers(B, O, ctx):
+    """30 k seeds = four pipeline chunks; validation runs inside the chunk workers, so a bad seed deep in the batch must
+    still fail the call with its own index, and a bad base code with the flank it sits in."""
+    t = B.synth_tasks("cfg2_150bp", 60000, seed=31)
+    seeds = seeds_from_flat(t, 30000, unset_score_every=3)
+    P2 = B.make_params2(B.make_params(), w=100, pen_clip5=5, pen_clip3=5)
+    want, _ = oracle_chain2aln(O, B, P2, seeds)
+    got = ctx.proc_element_batch(P2, seeds)
+    assert_same(want, got, "30 k seeds")
+    bad = dict(seeds[20000]); bad["h0"] = 0                          # a left flank with h0 < 1
+    if len(bad["q_left"]) == 0:
+        bad = dict(seeds[20001]); bad["h0"] = 0; k = 20001
+    else:
+        k = 20000
+    broken = list(seeds); broken[k] = bad
+    with pytest.raises(B.BswError) as e:
+        ctx.proc_element_batch(P2, broken)
+    assert e.value.code == B.BSW_EINVAL and f"seed task {k}" in str(e.value)
+    k = next(i for i in range(25000, 30000) if len(seeds[i]["q_right"]) > 3)
+    bad = dict(seeds[k]); qr = np.array(bad["q_right"], dtype=np.uint8).copy(); qr[2] = 7; bad["q_right"] = qr
+    broken = list(seeds); broken[k] = bad
+    with pytest.raises(B.BswError) as e:
+        ctx.proc_element_batch(P2, broken)
+    assert e.value.code == B.BSW_EINVAL and f"seed task {k}" in str(e.value) and "right flank" in str(e.value)
+    assert_same(want, ctx.proc_element_batch(P2, seeds), "the context still works after the failed calls")
+
+
 def test_level3_wire_format(B, O, ctx):
     """TBB image in, RBB image out (the FPGA has no z-drop and a fixed +1/-4/-1 matrix: compare with zdrop=0)."""
     t = B.synth_tasks("cfg1_101bp", 1600, seed=30)
