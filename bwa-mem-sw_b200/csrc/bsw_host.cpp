@@ -390,6 +390,29 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
     return 0;
 }
 
+// Runs fn(0..n-1) on n threads (the caller is worker 0).  Creating a thread costs ~17 us, so the second half of the
+// workers is created by the first spawned thread while the caller creates the first half: the last worker starts after
+// ~n/2 creations instead of n (0.3 -> 0.15 ms for 16 workers, which matters for 100 k task batches of ~1 ms).
+template <class F>
+void run_workers(size_t n, F& fn)
+{
+    if (n <= 1) { fn(0); return; }
+    const size_t half = n >= 6 ? (n + 1) / 2 : n;        // workers [half, n) belong to the helper
+    std::thread helper;
+    if (half < n)
+        helper = std::thread([&fn, half, n]() {
+            std::vector<std::thread> th;
+            for (size_t k = half + 1; k < n; ++k) th.emplace_back([&fn, k]() { fn(k); });
+            fn(half);
+            for (auto& t : th) t.join();
+        });
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < half; ++k) th.emplace_back([&fn, k]() { fn(k); });
+    fn(0);
+    for (auto& t : th) t.join();
+    if (helper.joinable()) helper.join();
+}
+
 Worker* get_worker(bsw_ctx* ctx, size_t k)
 {
     while (ctx->workers.size() <= k) {
@@ -511,13 +534,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         cudaEventRecord(ctx->trace_ref, ctx->devs[0].aux.stream);
         fprintf(stderr, "gpu timeline origin at host %.3f ms\n", now_ms() - w0);
     }
-    if (nworkers == 1) worker_main(0);
-    else {
-        std::vector<std::thread> th;
-        for (size_t k = 1; k < nworkers; ++k) th.emplace_back(worker_main, k);
-        worker_main(0);
-        for (auto& t : th) t.join();
-    }
+    run_workers(nworkers, worker_main);
     cudaSetDevice(prev_dev);
     {
         std::lock_guard<std::mutex> g(ctx->err_mu);
@@ -969,13 +986,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     };
     int prev_dev = 0;
     cudaGetDevice(&prev_dev);
-    if (nworkers == 1) worker_main(0);
-    else {
-        std::vector<std::thread> th;
-        for (size_t k = 1; k < nworkers; ++k) th.emplace_back(worker_main, k);
-        worker_main(0);
-        for (auto& t : th) t.join();
-    }
+    run_workers(nworkers, worker_main);
     cudaSetDevice(prev_dev);
     {
         std::lock_guard<std::mutex> g(ctx->err_mu);
