@@ -82,8 +82,18 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
 // order[] = task indices by ascending 32-bit key (stable LSD radix).  The digit width follows the chunk size: three
 // 11-bit passes for the usual 8-32 k task chunk (the three histograms come from one pass over the keys and stay in
 // L1), two 16-bit passes for big plans (resident batches) where the per-pass traffic dominates.
-static void radix_order(const uint32_t* key, size_t n, std::vector<uint32_t>& order, std::vector<uint32_t>& tmp, std::vector<uint32_t>& hist)
+static void radix_order(const uint32_t* key, size_t n, std::vector<uint32_t>& order, std::vector<uint32_t>& tmp, std::vector<uint32_t>& hist,
+                        bool key22 = false)
 {
+    if (key22) {                                       // keys below 2^22: two 11-bit passes
+        hist.assign(2 * 2049, 0);
+        uint32_t* h0 = hist.data(); uint32_t* h1 = h0 + 2049;
+        for (size_t i = 0; i < n; ++i) { const uint32_t k = key[i]; ++h0[(k & 2047u) + 1]; ++h1[(k >> 11) + 1]; }
+        for (size_t b = 0; b < 2048; ++b) { h0[b + 1] += h0[b]; h1[b + 1] += h1[b]; }
+        for (size_t i = 0; i < n; ++i) tmp[h0[key[i] & 2047u]++] = (uint32_t)i;
+        for (size_t i = 0; i < n; ++i) { const uint32_t t = tmp[i]; order[h1[key[t] >> 11]++] = t; }
+        return;
+    }
     if (n > ((size_t)1 << 17)) {
         hist.assign(2 * 65537, 0);
         uint32_t* h0 = hist.data(); uint32_t* h1 = h0 + 65537;
@@ -138,7 +148,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     // costs (rows of its longest lane) x (width of its widest live window).  The window of a row is about min(qlen, h0)
     // wide (the non-zero run around the diagonal grows with the score budget): tlen * min(qlen, h0) predicts the cell
     // count of a 150 bp task with correlation 0.99 (tools/tile_efficiency.py).
-    //   chunk plans (< 100 k tasks), K1 classes: [class:3][qlen/16:11][min(qlen,h0)/4:9][tlen/4:9] -- a coarse qlen
+    //   chunk plans (< 100 k tasks), K1 classes: [class:3][qlen/16:7][min(qlen,h0)/4:6][tlen/8:6] (22 bits) -- a coarse qlen
     //       bucket (it sets the tile's shared memory, i.e. the occupancy bucket), then the window width, then the rows.
     //       Lane efficiency of 16 k task chunks (row-lockstep model) against the key below: 150 bp reads 0.89 -> 0.96,
     //       50-250 bp mix 0.67 -> 0.87; measured e2e on 1 M tasks 6.45 -> 5.85 ms and 11.9 -> 8.3 ms.
@@ -150,20 +160,31 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
     key.resize(n); order.resize(n); tmp.resize(n);
     const bool width_key = n < 100000;
-    for (size_t i = 0; i < n; ++i) {
-        const ExtTask& t = tasks[i];
-        const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
-        if ((cls[i] & 2u) || !width_key) {
+    if (width_key) {
+        // 22-bit keys (two radix passes): [class:3][qlen/16:7][min(qlen,h0)/4:6][tlen/8:6]; K2 classes [class:3][qlen/128:7][tlen/512:12]
+        for (size_t i = 0; i < n; ++i) {
+            const ExtTask& t = tasks[i];
+            const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
+            if (cls[i] & 2u) {
+                const uint32_t ql = (uint32_t)std::min(t.qlen >> 7, 127), tl = (uint32_t)std::min(t.tlen >> 9, 4095);
+                key[i] = (c << 19) | ((127u - ql) << 12) | (4095u - tl);
+            } else {
+                const uint32_t qb = (uint32_t)std::min(t.qlen >> 4, 127);
+                const uint32_t wd = (uint32_t)std::min(std::min(t.qlen, t.h0) >> 2, 63), tl = (uint32_t)std::min(t.tlen >> 3, 63);
+                key[i] = (c << 19) | ((127u - qb) << 12) | ((63u - wd) << 6) | (63u - tl);
+            }
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i) {
+            const ExtTask& t = tasks[i];
+            const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
             const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 3, 8191) : (uint32_t)std::min(t.qlen, 8191);
             const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
             key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
-        } else {
-            const uint32_t qb = (uint32_t)std::min(t.qlen >> 4, 2047);
-            const uint32_t wd = (uint32_t)std::min(std::min(t.qlen, t.h0) >> 2, 511), tl = (uint32_t)std::min(t.tlen >> 2, 511);
-            key[i] = (c << 29) | ((2047u - qb) << 18) | ((511u - wd) << 9) | (511u - tl);
         }
     }
-    radix_order(key.data(), n, order, tmp, hist);
+    const int class_shift = width_key ? 19 : 29;
+    radix_order(key.data(), n, order, tmp, hist, width_key);
 
     // new occupancy bucket (= new launch) when a tile would fit at >= 1.15x the CTAs/SM of the current bucket (big plans;
     // measured best with the launches spread over four streams), >= 1.3x (100-400 k tasks) or >= 2x (the chunks of the
@@ -182,9 +203,9 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     };
     size_t i = 0;
     while (i < n) {
-        const uint32_t c = key[order[i]] >> 29;
+        const uint32_t c = key[order[i]] >> class_shift;
         size_t cend = i;
-        while (cend < n && (key[order[cend]] >> 29) == c) ++cend;
+        while (cend < n && (key[order[cend]] >> class_shift) == c) ++cend;
         const bool is_k2 = c >= 4u;
         const bool is_ring = (c & 6u) == 2u;
         const bool is_pair = c == 0u && opt.pair && opt.variant == 1;
