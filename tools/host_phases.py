@@ -5,7 +5,7 @@ E.bsw_emu_host_phases.argtypes=[C.POINTER(B.Params)]+[C.c_void_p]*6+[C.c_size_t,
 n=1000000
 t=B.synth_tasks("cfg2_150bp", n)
 p=B.make_params()
-for th,ch in ((1,32768),(16,32768),(16,16384)):
+for th,ch in ((1,16384),(2,16384),(4,16384),(8,16384),(12,16384),(16,16384)):
   for rep in range(3):
     ms=np.zeros(8)
     rc=E.bsw_emu_host_phases(C.byref(p), t['qbuf'].ctypes.data,t['qoff'].ctypes.data,t['tbuf'].ctypes.data,t['toff'].ctypes.data,t['h0'].ctypes.data,t['w'].ctypes.data,n,th,ch,ms.ctypes.data)
