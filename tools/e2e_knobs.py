@@ -12,8 +12,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     out = np.zeros(n, dtype=B.RESULT_DTYPE)
     tag = " ".join("%s=%s" % (k, os.environ.get(k)) for k in ("CUDA_DEVICE_MAX_CONNECTIONS", "BSW_BUCKET_PCT", "BSW_SIDE_STREAMS"))
-    for slots in (2, 4):
-        for chunk in (16384, 32768):
+    for slots in (2, 3):
+        for chunk in (8192, 12288, 16384, 24576):
             ctx.set_option("slots", slots); ctx.set_option("chunk_tasks", chunk)
             for _ in range(3): ctx.sw_extend_batch(p, *flat, want_cells=False, out=out)
             ts = []
