@@ -177,6 +177,7 @@ def main():
     p = B.make_params()
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     alg_bytes = int((t["qoff"][-1] + t["toff"][-1] + 1) // 2 + n * (16 + 32))   # 4-bit bases + slot scalars + result record
+    cells_rect = float((np.diff(t["qoff"]).astype(np.float64) * np.diff(t["toff"]).astype(np.float64)).sum())   # sum of qlen*tlen
 
     peak = ctx.measure_int_peak(0) if rank == 0 else None
     res = ctx.resident(p, *flat)
@@ -215,16 +216,16 @@ def main():
     st = ctx.stats()
 
     # ---------------- max over ranks ----------------
-    agg = torch.tensor([dev_ms, e2e_s, float(cells), float(launches)], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([dev_ms, e2e_s, float(cells), float(launches), cells_rect], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = agg.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = agg.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s = float(mx[0]), float(mx[1])
-        cells_all, launches_all = float(sm[2]), int(sm[3])
+        cells_all, launches_all, rect_all = float(sm[2]), int(sm[3]), float(sm[4])
     else:
-        cells_all, launches_all = float(cells), launches
+        cells_all, launches_all, rect_all = float(cells), launches, cells_rect
     if rank == 0:
         steps = args.steps
         default_wl = args.workload == "cfg2_150bp" and n == 1_000_000
@@ -243,11 +244,13 @@ def main():
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16x2/int32", "data": "synthetic",
             "tasks_per_s": n * world * steps / (dev_ms * 1e-3),
+            "gcups_rect": rect_all * steps / (dev_ms * 1e-3) * 1e-9,    # qlen*tlen cells, for comparison with the literature
             "config": {"workload": f"{args.workload}: {n} synthetic extension tasks per GPU per step (BASELINE.json configs[1] generator)",
                        "scoring": "a=1 b=4 o=6 e=1 w=100 zdrop=100 end_bonus=5", "variant": "V1 (RTL / BWA 0.7.8 recurrence)",
                        "l2": "256 MB flush write between timed steps", "cells_per_step_per_gpu": int(cells),
                        "timing": "value = sum of CUDA-event durations of the kernel launches on the library stream; e2e = wall clock around the blocking C-ABI call"},
-            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "tasks_per_s": n * world * steps / e2e_s, "ms_per_step": e2e_s / steps * 1e3,
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "gcups_rect": rect_all * steps / e2e_s * 1e-9,
+                    "tasks_per_s": n * world * steps / e2e_s, "ms_per_step": e2e_s / steps * 1e3,
                     "h2d_bytes_per_step": int(st["h2d_bytes"] // steps), "d2h_bytes_per_step": int(st["d2h_bytes"] // steps),
                     "host_pack_ms_per_step": st["pack_ms"] / steps, "host_threads": host_threads},
             "gpu_launches": launches_all,
