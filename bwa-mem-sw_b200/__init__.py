@@ -157,6 +157,8 @@ def lib() -> C.CDLL:
         L.bsw_resident_run.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
         L.bsw_resident_fetch.argtypes = [vp, vp, vp, vp]
         L.bsw_resident_free.argtypes = [vp, vp]; L.bsw_resident_free.restype = None
+        L.bsw_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.bsw_host_unregister.argtypes = [vp, vp]
         L.bsw_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.bsw_reset_stats.argtypes = [vp]
         L.bsw_measure_int_peak.argtypes = [vp, i32, C.POINTER(IntPeak)]
@@ -240,6 +242,15 @@ class Context:
         return lib().bsw_num_devices(self.handle)
 
     # ---- level 1: sw_extend ----
+    def register_host(self, arr: np.ndarray) -> None:
+        """Page-lock a long-lived uint8 base buffer in place (bsw_host_register): flat batches whose bases live in
+        registered buffers skip the host staging pass.  Keep the array alive until unregister_host / close."""
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        self._check(lib().bsw_host_register(self.handle, arr.ctypes.data, arr.nbytes))
+
+    def unregister_host(self, arr: np.ndarray) -> None:
+        self._check(lib().bsw_host_unregister(self.handle, arr.ctypes.data))
+
     def sw_extend_batch(self, params: Params, qbuf, qoff, tbuf, toff, h0, w, want_cells: bool = True, out=None, cells=None):
         """Flat layout: task i's query is qbuf[qoff[i]:qoff[i+1]].  Returns (results[RESULT_DTYPE], cells[uint32]).
         out / cells: optional caller-owned result arrays (the C ABI writes into caller buffers; reuse them across calls)."""

@@ -60,6 +60,11 @@ struct GatherArgs {
     const uint32_t*  src;          // task-major source arena (H2D copy of the host packer's output)
     uint32_t*        dst;          // tiled arena
     uint32_t         ntiles;
+    // raw mode (the caller's bases were copied as they are, one code per byte, from registered host memory): SlotSrc then
+    // holds BYTE offsets into raw_q / raw_t, the gather packs the nibbles itself and reports per slot what it saw
+    const uint8_t*   raw_q;
+    const uint8_t*   raw_t;
+    uint32_t*        slot_flags;   // per slot: SLOT_HAS_N | SLOT_BAD_CODE
 };
 
 // Per-seed scalars of the fused level-2 kernel K3 (one FPGA PE task: sw_pe_array_proc_element.v:1593-1685).
@@ -76,6 +81,7 @@ struct LaunchArgs {
     const uint32_t*  arena;        // K1: tiled arena; K2: source arena (16-byte aligned blocks)
     SlotResult*      out;          // indexed by out_index[slot] (the chunk's task order), or by slot when out_index is null
     const uint32_t*  out_index;
+    const uint32_t*  slot_flags;   // raw mode: what the gather saw in the slot's bases (null otherwise)
     unsigned long long* cells_total;   // device counter of evaluated DP cells (one atomic per warp), may be null
     DevParams        p;
     uint32_t         ntiles;
@@ -90,6 +96,9 @@ struct LaunchArgs {
 
 constexpr int STATUS_OK = 0;
 constexpr int STATUS_OVERFLOW = 1;  // K1R: the live window outgrew the ring; the host reruns the task on K2
+constexpr int STATUS_HAS_N = 2;     // raw mode: the task holds an N and ran on the +a/-b kernel; the host reruns it with matrix lookup
+constexpr int STATUS_BAD_CODE = 3;  // raw mode: a base code above 4
+constexpr uint32_t SLOT_HAS_N = 1u, SLOT_BAD_CODE = 2u;
 constexpr int K1R_RING = 512;       // columns of K1R's row ring
 constexpr uint32_t TILE_ONEHOT = 0x8000u;   // TileHdr.nqw_ntw bit 15: the query block holds match planes (K0 builds them)
 

@@ -50,6 +50,11 @@ struct Slot {
     uint32_t* d_arena = nullptr;  size_t d_arena_cap = 0;     // tiled arena, written by the k0 gather kernel
     SlotResult* d_out = nullptr;  size_t d_out_cap = 0;
     size_t src_words = 0;
+    // raw mode: the chunk's bases as the caller holds them (one code per byte) and the gather's per-slot findings
+    unsigned char* d_rawq = nullptr; size_t d_rawq_cap = 0;
+    unsigned char* d_rawt = nullptr; size_t d_rawt_cap = 0;
+    uint32_t* d_flags = nullptr;     size_t d_flags_cap = 0;
+    bool raw_mode = false;
     const uint32_t*  d_src() const { return reinterpret_cast<const uint32_t*>(d_in); }
     const TileHdr*   d_tiles() const { return reinterpret_cast<const TileHdr*>(d_in + off_tiles); }
     const SlotParam* d_slots() const { return reinterpret_cast<const SlotParam*>(d_in + off_slots); }
@@ -87,6 +92,9 @@ struct Device {
 struct TaskSource {
     const void* self;
     void (*fill)(const void* self, size_t first, size_t count, ExtTask* out);
+    // raw mode: the bases of consecutive tasks are consecutive in two buffers the caller registered with bsw_host_register
+    // (so the DMA engine can read them in place); a chunk's bases are then the byte ranges [task first .q, last .q + qlen)
+    bool raw = false;
 };
 
 }  // namespace
@@ -97,7 +105,9 @@ struct bsw_ctx {
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 16384;
-    int slots_per_worker = 2;      // chunks one worker keeps in flight
+    int slots_per_worker = 2;
+    bool raw_inputs = true;        // flat batches whose base buffers are registered (bsw_host_register) skip the host packer
+    std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     cudaEvent_t trace_ref = nullptr;   // BSW_TRACE: recorded at the start of a batch call, origin of the per-chunk GPU timeline
@@ -194,6 +204,9 @@ void slot_free(Slot& s)
     if (s.d_arena) cudaFree(s.d_arena);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_cells) cudaFree(s.d_cells);
+    if (s.d_rawq) cudaFree(s.d_rawq);
+    if (s.d_rawt) cudaFree(s.d_rawt);
+    if (s.d_flags) cudaFree(s.d_flags);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -257,7 +270,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
     }
     for (const Launch& L : P.launches) {
         LaunchArgs a{};
-        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index;
+        a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index; a.slot_flags = s.raw_mode ? s.d_flags : nullptr;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
         const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
@@ -285,6 +298,7 @@ int enqueue_gather(bsw_ctx* ctx, Slot& s)
     if (!P.n_k1_tiles) return 0;
     GatherArgs g{};
     g.tiles = s.d_tiles(); g.slots = s.d_slots(); g.slot_src = s.d_ssrc(); g.src = s.d_src(); g.dst = s.d_arena; g.ntiles = P.n_k1_tiles;
+    if (s.raw_mode) { g.raw_q = s.d_rawq; g.raw_t = s.d_rawt; g.slot_flags = s.d_flags; }
     cudaError_t e = k0_launch(g, s.stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "K0 gather launch");
     return 0;
@@ -292,24 +306,57 @@ int enqueue_gather(bsw_ctx* ctx, Slot& s)
 
 // Pack + schedule the chunk held in s.tasks (tasks [first, first+count) of the batch) into the slot's pinned staging,
 // then enqueue H2D, the k0 gather, the extension kernels and D2H on the slot's stream.
+// Raw mode takes a chunk as it is when every task is a plain inter-task (K1) extension with valid scalars; anything else
+// (long tasks, bad lengths, ...) goes through the staged path, which also words the error messages.
+bool raw_chunk_eligible(const ExtTask* t, size_t count, int max_mat, const SchedOptions& opt)
+{
+    if (opt.force_kernel == 2 || opt.pair || count == 0) return false;
+    const uint8_t* q0 = t[0].q; const uint8_t* t0 = t[0].t;
+    if (!q0 || !t0) return false;
+    for (size_t i = 0; i < count; ++i) {
+        const ExtTask& x = t[i];
+        if (!x.q || !x.t || x.qlen < 1 || x.tlen < 1 || x.h0 < 1 || x.w < 0) return false;
+        if ((int64_t)x.h0 + (int64_t)x.qlen * max_mat > SCORE_CAP || x.tlen > 500000) return false;
+        if (x.qlen > K1_QLEN_CAP || (opt.force_kernel == 0 && x.qlen >= opt.k2_min_qlen)) return false;
+        if (x.q < q0 || x.t < t0) return false;                                   // offsets are taken from the first task
+    }
+    const ExtTask& l = t[count - 1];
+    return (l.q + l.qlen - q0) < (ptrdiff_t)0x7fff0000 && (l.t + l.tlen - t0) < (ptrdiff_t)0x7fff0000;
+}
+
 int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, const DevParams& dp, int sym,
-                const SchedOptions& opt, bool timing, LocalStats* st)
+                const SchedOptions& opt, bool timing, LocalStats* st, bool raw = false)
 {
     const double t0 = now_ms();
     int rc;
+    s.raw_mode = raw;
     // upper bounds of the input block: nslots <= count + 4 classes * 31 padding lanes, tiles <= count + 4
-    const size_t src_bound = source_arena_bound(s.tasks.data(), count) * 4;
+    const size_t src_bound = raw ? 0 : source_arena_bound(s.tasks.data(), count) * 4;
     const size_t max_slots = count + 4 * TILE_LANES, max_tiles = count + 4;
     const size_t in_bound = src_bound + max_tiles * sizeof(TileHdr) + max_slots * (sizeof(SlotParam) + sizeof(SlotSrc) + sizeof(uint32_t)) + 64;
     if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bound))) return rc;
     s.cls.resize(count); s.src.resize(count);
-    size_t bad = 0; std::string msg;
-    rc = pack_tasks(s.tasks.data(), count, max_mat, opt, s.cls.data(), s.src.data(), reinterpret_cast<uint32_t*>(s.h_in),
-                    &s.src_words, &bad, &msg);
-    if (rc) {
-        const size_t colon = msg.find(':');
-        set_error(ctx, "task " + std::to_string(first + bad) + (colon == std::string::npos ? "" : msg.substr(colon)));
-        return rc;
+    size_t raw_qbytes = 0, raw_tbytes = 0;
+    if (raw) {
+        // no staging: the bases stay where the caller has them; a slot's source is a byte offset into the chunk's ranges
+        const ExtTask* t = s.tasks.data();
+        const uint8_t cl = opt.fast_matrix ? 0 : 1;
+        for (size_t i = 0; i < count; ++i) {
+            s.cls[i] = cl;
+            s.src[i] = SlotSrc{ (uint32_t)(t[i].q - t[0].q), (uint32_t)(t[i].t - t[0].t) };
+        }
+        raw_qbytes = (size_t)(t[count - 1].q + t[count - 1].qlen - t[0].q);
+        raw_tbytes = (size_t)(t[count - 1].t + t[count - 1].tlen - t[0].t);
+        s.src_words = 0;
+    } else {
+        size_t bad = 0; std::string msg;
+        rc = pack_tasks(s.tasks.data(), count, max_mat, opt, s.cls.data(), s.src.data(), reinterpret_cast<uint32_t*>(s.h_in),
+                        &s.src_words, &bad, &msg);
+        if (rc) {
+            const size_t colon = msg.find(':');
+            set_error(ctx, "task " + std::to_string(first + bad) + (colon == std::string::npos ? "" : msg.substr(colon)));
+            return rc;
+        }
     }
     const double t1 = now_ms();
     build_plan(s.tasks.data(), s.cls.data(), s.src.data(), count, opt, &s.plan);
@@ -325,6 +372,11 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
     if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.tiled_words))) return rc;
     if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, count))) return rc;      // results come back in task order
+    if (raw) {
+        if ((rc = grow_device(ctx, &s.d_rawq, &s.d_rawq_cap, raw_qbytes + 32))) return rc;       // + the gather's 15-byte over-read
+        if ((rc = grow_device(ctx, &s.d_rawt, &s.d_rawt_cap, raw_tbytes + 32))) return rc;
+        if ((rc = grow_device(ctx, &s.d_flags, &s.d_flags_cap, nslots))) return rc;
+    }
     memcpy(s.h_in + s.off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
     memcpy(s.h_in + s.off_slots, P.slots.data(), nslots * sizeof(SlotParam));
     memcpy(s.h_in + s.off_ssrc, P.slot_src.data(), nslots * sizeof(SlotSrc));
@@ -337,6 +389,10 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     // per chunk: 1 H2D, 1 gather, the bucket launches, 1 D2H, 1 event (the per-task cells come back in the records)
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_in, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (raw) {                                           // straight from the caller's registered buffers
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawq, s.tasks[0].q, raw_qbytes, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawt, s.tasks[0].t, raw_tbytes, cudaMemcpyHostToDevice, s.stream));
+    }
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if ((rc = enqueue_gather(ctx, s))) return rc;
     if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub, s.d_oidx()))) return rc;
@@ -350,14 +406,15 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     st->validate_ms += t1 - t0;
     st->pack_ms += t2 - t1;
     s.trace_ms[0] = t1 - t0; s.trace_ms[1] = t2 - t1; s.trace_ms[2] = now_ms() - t2;
-    st->h2d += s.in_bytes;
+    st->h2d += s.in_bytes + raw_qbytes + raw_tbytes;
     st->d2h += count * sizeof(SlotResult);
     st->launches += s.nlaunch;
     return 0;
 }
 
 // Wait for the slot's chunk and scatter its results to out[first + task].
-int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow)
+int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow,
+                 std::vector<size_t>* rerun_n)
 {
     if (!s.busy) return 0;
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
@@ -378,6 +435,11 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
     for (size_t t = 0; t < count; ++t) {
         const SlotResult& r = h_out[t];
         if (r.status == STATUS_OVERFLOW) { overflow->push_back(first + t); continue; }     // K1R ring too small: rerun on K2
+        if (r.status == STATUS_HAS_N) { rerun_n->push_back(first + t); continue; }         // raw mode: rerun with matrix lookup
+        if (r.status == STATUS_BAD_CODE) {
+            set_error(ctx, "task " + std::to_string(first + t) + ": invalid (base code > 4)");
+            return BSW_EINVAL;
+        }
         if (r.status != STATUS_OK) bad = 1;
         cell_sum += (uint32_t)r.cells;
         bsw_result& o = out[first + t];
@@ -429,7 +491,7 @@ Worker* get_worker(bsw_ctx* ctx, size_t k)
 // multi-GPU context balances dynamically -- the GPU analogue of task_parse handing the next task to the first PE
 // with room (sw_pe_array_task_parse.v:1600-1650).  No collective: results land in out[task].
 int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out,
-                          uint32_t* cells, int force_kernel, std::vector<size_t>* overflow_out)
+                          uint32_t* cells, int force_kernel, std::vector<size_t>* overflow_out, std::vector<size_t>* rerun_n_out = nullptr)
 {
     const double w0 = now_ms();
     DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
@@ -477,12 +539,13 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     std::atomic<int> first_err(0);
     std::mutex stat_mu;
     LocalStats total;
-    std::vector<size_t> overflow_all;
+    std::vector<size_t> overflow_all, rerun_all;
+    const bool allow_raw = src.raw && rerun_n_out != nullptr && ctx->raw_inputs;
 
     auto worker_main = [&](size_t k) {
         Worker& W = *ctx->workers[k];
         LocalStats st;
-        std::vector<size_t> ovf;
+        std::vector<size_t> ovf, rrn;
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
         if (!r && W.slots.size() < (size_t)ctx->slots_per_worker) {
@@ -502,14 +565,15 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
             Slot& s = W.slots[cur];
             cur = (cur + 1) % nslot;
             const double c0 = T();
-            if ((r = slot_collect(ctx, s, out, cells, &st, &ovf))) break;
+            if ((r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn))) break;
             if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(first) + "+" + std::to_string(count) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
             const double v0 = now_ms();
             s.tasks.resize(count);
             src.fill(src.self, first, count, s.tasks.data());
             st.validate_ms += now_ms() - v0;
             const double f1 = T();
-            r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st);
+            const bool raw = allow_raw && raw_chunk_eligible(s.tasks.data(), count, max_mat, opt);
+            r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, raw);
             if (trace) tr += " fill.." + std::to_string(f1) + " submitted " + std::to_string(T()) + " (pack " + std::to_string(s.trace_ms[0]) +
                              " plan " + std::to_string(s.trace_ms[1]) + " api " + std::to_string(s.trace_ms[2]) + ")\n";
         }
@@ -517,12 +581,13 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         for (size_t q = 0; q < W.slots.size(); ++q) {                                    // oldest chunk first
             Slot& s = W.slots[(cur + q) % W.slots.size()];
             if (r) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }    // leave the device quiescent
-            else r = slot_collect(ctx, s, out, cells, &st, &ovf);
+            else r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn);
         }
         if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
         if (trace) { tr += " done " + std::to_string(T()) + "\n"; fputs(tr.c_str(), stderr); }
         std::lock_guard<std::mutex> g(stat_mu);
         overflow_all.insert(overflow_all.end(), ovf.begin(), ovf.end());
+        rerun_all.insert(rerun_all.end(), rrn.begin(), rrn.end());
         total.pack_ms += st.pack_ms; total.validate_ms += st.validate_ms; total.kernel_ms += st.kernel_ms;
         total.h2d += st.h2d; total.d2h += st.d2h; total.launches += st.launches; total.tasks += st.tasks; total.cells += st.cells;
     };
@@ -544,9 +609,10 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         S.h2d_bytes += total.h2d; S.d2h_bytes += total.d2h; S.kernel_ms += total.kernel_ms;
         S.pack_ms += (total.pack_ms + total.validate_ms) / (double)nworkers;     // average per worker = wall share
         S.wall_ms += now_ms() - w0;
-        S.tasks -= overflow_all.size();          // counted again by the rerun
+        S.tasks -= overflow_all.size() + rerun_all.size();          // counted again by the reruns
     }
     if (overflow_out) overflow_out->swap(overflow_all);
+    if (rerun_n_out) rerun_n_out->swap(rerun_all);
     return first_err.load();
 }
 
@@ -563,17 +629,23 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
     if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (n == 0) return BSW_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    std::vector<size_t> overflow;
-    int rc = run_extensions_locked(ctx, params, src, n, out, cells, -1, &overflow);
-    if (rc || overflow.empty()) return rc;
-    // K1R tasks whose live window outgrew the ring: rerun them on K2 (whole task, from scratch) and scatter
-    std::sort(overflow.begin(), overflow.end());
-    const SubsetSrc sub{ &src, overflow.data() };
-    std::vector<bsw_result> r2(overflow.size());
-    std::vector<uint32_t> c2(cells ? overflow.size() : 0);
-    rc = run_extensions_locked(ctx, params, TaskSource{ &sub, fill_subset }, overflow.size(), r2.data(), cells ? c2.data() : nullptr, 2, nullptr);
+    std::vector<size_t> overflow, rerun_n;
+    int rc = run_extensions_locked(ctx, params, src, n, out, cells, -1, &overflow, &rerun_n);
     if (rc) return rc;
-    for (size_t k = 0; k < overflow.size(); ++k) { out[overflow[k]] = r2[k]; if (cells) cells[overflow[k]] = c2[k]; }
+    // K1R tasks whose live window outgrew the ring are rerun on K2, raw-mode tasks that hold an N on the staged path (which
+    // classifies them for the matrix-lookup kernel): whole tasks, from scratch, results scattered over the first pass
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<size_t>& list = pass ? rerun_n : overflow;
+        if (list.empty()) continue;
+        std::sort(list.begin(), list.end());
+        const SubsetSrc sub{ &src, list.data() };
+        std::vector<bsw_result> r2(list.size());
+        std::vector<uint32_t> c2(cells ? list.size() : 0);
+        rc = run_extensions_locked(ctx, params, TaskSource{ &sub, fill_subset }, list.size(), r2.data(), cells ? c2.data() : nullptr,
+                                   pass ? -1 : 2, nullptr);
+        if (rc) return rc;
+        for (size_t k = 0; k < list.size(); ++k) { out[list[k]] = r2[k]; if (cells) cells[list[k]] = c2[k]; }
+    }
     return BSW_OK;
 }
 
@@ -613,6 +685,14 @@ void fill_records(const void* self, size_t first, size_t count, ExtTask* out)
 void fill_vector(const void* self, size_t first, size_t count, ExtTask* out)
 {
     memcpy(out, static_cast<const ExtTask*>(self) + first, count * sizeof(ExtTask));
+}
+
+bool host_range_registered(bsw_ctx* ctx, const unsigned char* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    for (const auto& r : ctx->host_regs)
+        if (p >= r.first && p + bytes <= r.first + r.second) return true;
+    return false;
 }
 
 }  // namespace
@@ -681,6 +761,7 @@ void bsw_destroy(bsw_ctx* ctx)
         if (D.aux.stream) cudaStreamSynchronize(D.aux.stream);
         slot_free(D.aux);
     }
+    for (const auto& r : ctx->host_regs) cudaHostUnregister(const_cast<unsigned char*>(r.first));
     cudaSetDevice(prev);
     delete ctx;
 }
@@ -696,6 +777,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     const std::string k(key);
     if (k == "variant") { if (value != 1 && value != 2) return BSW_EINVAL; ctx->opt.variant = (int)value; }
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
+    else if (k == "raw_inputs") { ctx->raw_inputs = value != 0; }
     else if (k == "slots") { if (value < 1 || value > 16) return BSW_EINVAL; ctx->slots_per_worker = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
@@ -731,7 +813,45 @@ int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t*
     if (params->e_ins < 1 || params->e_del < 1) { set_error(ctx, "gap extension must be >= 1"); return BSW_EINVAL; }
     const BandClamp clamp(params->mat, params->end_bonus, params->o_ins, params->e_ins, params->o_del, params->e_del);
     const FlatSrc S{ params, &clamp, qbuf, qoff, tbuf, toff, h0, w };
-    return run_extensions(ctx, params, TaskSource{ &S, fill_flat }, n, out, cells);
+    TaskSource src{ &S, fill_flat };
+    // bases in registered host memory: the DMA engine reads them in place and the device packs them (raw mode)
+    if (qoff[n] >= qoff[0] && toff[n] >= toff[0])
+        src.raw = host_range_registered(ctx, qbuf + qoff[0], (size_t)(qoff[n] - qoff[0])) &&
+                  host_range_registered(ctx, tbuf + toff[0], (size_t)(toff[n] - toff[0]));
+    return run_extensions(ctx, params, src, n, out, cells);
+}
+
+/* Registered host memory: page-locked in place (cudaHostRegister), so that batches whose bases live there are copied by
+ * the DMA engine without the staging pass.  Ranges are remembered per context. */
+int bsw_host_register(bsw_ctx* ctx, const void* ptr, size_t bytes)
+{
+    if (!ctx || !ptr || !bytes) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->devs[0].id);
+    const cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(ctx, e, "cudaHostRegister"); }
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    ctx->host_regs.emplace_back(static_cast<const unsigned char*>(ptr), bytes);
+    return BSW_OK;
+}
+
+int bsw_host_unregister(bsw_ctx* ctx, const void* ptr)
+{
+    if (!ctx || !ptr) return BSW_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        auto it = std::find_if(ctx->host_regs.begin(), ctx->host_regs.end(),
+                               [&](const std::pair<const unsigned char*, size_t>& r) { return r.first == ptr; });
+        if (it == ctx->host_regs.end()) { ctx->last_error = "bsw_host_unregister: not a registered range"; return BSW_EINVAL; }
+        ctx->host_regs.erase(it);
+    }
+    const cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(ctx, e, "cudaHostUnregister"); }
+    return BSW_OK;
 }
 
 // ---------------- level 2: fused seed task (left + right extension, band retry, clip) ----------------

@@ -50,6 +50,38 @@ __device__ __forceinline__ void k0_copy_planes(const uint4* __restrict__ src16, 
     }
 }
 
+// Raw mode: the lane's sequence is `len` bytes (one base code each) at an arbitrary byte address.  Eight bases per step:
+// one aligned 8-byte load (the previous one supplies the low part), nibble pack, and two SWAR tests -- any byte above 4,
+// any byte equal to 4.  Reads run at most 15 bytes past the sequence (the raw buffers carry that slack).
+__device__ __forceinline__ uint32_t k0_pack_raw(const uint8_t* __restrict__ base, int len, uint32_t* __restrict__ dst,
+                                                int tile_words, int lane)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    const int sh = (int)(a & 7u) * 8;
+    uint32_t flags = 0;
+    unsigned long long lo = len > 0 ? __ldg(p) : 0ull;
+    for (int k = 0; k < tile_words; ++k) {
+        uint32_t w = 0;
+        if (8 * k < len) {
+            const unsigned long long hi = __ldg(p + k + 1);
+            unsigned long long v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+            lo = hi;
+            const int rem = len - 8 * k;
+            if (rem < 8) v &= (1ull << (8 * rem)) - 1ull;
+            if ((v | (v + 0x7b7b7b7b7b7b7b7bull)) & 0x8080808080808080ull) flags |= SLOT_BAD_CODE;       // some byte >= 5
+            const unsigned long long z = v ^ 0x0404040404040404ull;                                      // zero byte <=> code 4
+            if ((z - 0x0101010101010101ull) & ~z & 0x8080808080808080ull) flags |= SLOT_HAS_N;
+            unsigned long long x = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
+            x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+            x = (x | (x >> 16));
+            w = (uint32_t)x;
+        }
+        dst[(size_t)k * TILE_LANES + lane] = w;
+    }
+    return flags;
+}
+
 __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_constant__ GatherArgs A)
 {
     const int lane = threadIdx.x & 31;
@@ -61,6 +93,12 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_c
     const SlotSrc ss = A.slot_src[hd.slot0 + lane];
     const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0;      // words the host packed for this task (zero padded)
     const int own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
+    if (A.raw_q) {
+        uint32_t f = k0_pack_raw(A.raw_q + ss.qoff16, sp.qlen, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
+        f |= k0_pack_raw(A.raw_t + ss.toff16, sp.tlen, A.dst + (size_t)hd.toff16 * 4, ntw, lane);
+        A.slot_flags[hd.slot0 + lane] = f;
+        return;
+    }
     const uint4* src16 = reinterpret_cast<const uint4*>(A.src);
     if (hd.nqw_ntw & TILE_ONEHOT) k0_copy_planes(src16 + ss.qoff16, own_q, sp.qlen, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
     else k0_copy_block(src16 + ss.qoff16, own_q, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);

@@ -63,6 +63,11 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
         const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u + lane;
         SlotResult r;
         k1_task<VARIANT, GENERIC, SYM>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, (int)nqw, eh + lane, qs + lane, tg, r);
+        if (A.slot_flags) {                              // raw mode: what the gather saw in this slot's bases
+            const uint32_t f = A.slot_flags[slot];
+            if (f & SLOT_BAD_CODE) r.status = STATUS_BAD_CODE;
+            else if (!GENERIC && (f & SLOT_HAS_N)) r.status = STATUS_HAS_N;      // the +a/-b cell cannot score an N
+        }
         int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
         o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
         o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);

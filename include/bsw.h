@@ -54,7 +54,8 @@ void bsw_destroy(bsw_ctx *ctx);
 const char *bsw_last_error(const bsw_ctx *ctx);          /* thread-unsafe convenience: last error text of this ctx */
 const char *bsw_version(void);
 /* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity, default 16384);
- * "slots" N (chunks one host worker keeps in flight, default 2);
+ * "slots" N (chunks one host worker keeps in flight, default 2); "raw_inputs" {0,1} use the no-staging path for
+ * registered buffers (default 1);
  * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
  * "k2_warps" {1,4} warps per K2 task; "fused_l2" {0,1} level 2 as one fused kernel (default 1);
  * experimental kernels, off by default because they measured slower: "k1_pair", "ring", "k2_sub";
@@ -85,6 +86,13 @@ typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } bsw_result;
 
 /* out[i] <-> tasks[i].  ONE band try per task with the given w (the MAX_BAND_TRY loop lives in level 2). */
 int bsw_extend_batch(bsw_ctx *ctx, const bsw_params *params, const bsw_task *tasks, size_t n, bsw_result *out);
+
+/* Registered host memory (optional).  A flat batch whose qbuf and tbuf ranges lie inside buffers registered here is
+ * not staged by host threads: the copy engine reads the bases in place (one code per byte) and the device packs them.
+ * The call page-locks the range (cudaHostRegister); register long-lived batch buffers once, not per call.  Tasks that
+ * hold an N are rerun on the staged path automatically; results and error codes are the same either way. */
+int bsw_host_register(bsw_ctx *ctx, const void *ptr, size_t bytes);
+int bsw_host_unregister(bsw_ctx *ctx, const void *ptr);
 
 /* Same, flat layout: task i's query is qbuf[qoff[i] .. qoff[i+1]), target likewise (n+1 offsets each).
  * cells (optional, may be NULL): per-task number of DP cells actually evaluated (sum over rows of end-beg). */

@@ -211,6 +211,64 @@ def test_level2_many_chunks_and_errors_found_by_the_workers(B, O, ctx):
     assert_same(want, ctx.proc_element_batch(P2, seeds), "the context still works after the failed calls")
 
 
+def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
+    """Raw mode: bases in registered host memory are copied in place and packed on the device.  Same results, per-task
+    cells and error codes as the staged path; tasks with N are rerun with matrix lookup; long tasks fall back."""
+    t = B.synth_tasks("cfg3_mixed", 40000, seed=41, n_frac=0.002)
+    p, po = B.make_params(), O.make_params()
+    flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    ro, co = O.extend_batch(po, *flat)
+    ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"])
+    try:
+        ctx.reset_stats()
+        r, c = ctx.sw_extend_batch(p, *flat)
+        st = ctx.stats()
+        assert_same(ro, r, "raw mode results"); assert_same(co.astype(np.int64), c.astype(np.int64), "raw mode cells")
+        assert st["h2d_bytes"] > int(t["qoff"][-1] + t["toff"][-1])            # the bases crossed PCIe one byte each
+        for variant in (2,):
+            ctx.set_option("variant", variant)
+            try:
+                r2, c2 = ctx.sw_extend_batch(p, *flat)
+            finally:
+                ctx.set_option("variant", 1)
+            ro2, co2 = O.extend_batch(po, *flat, variant=variant)
+            assert_same(ro2, r2, "raw mode V2"); assert_same(co2.astype(np.int64), c2.astype(np.int64), "raw mode V2 cells")
+        pk = dict(o_del=4, e_del=2, o_ins=7, e_ins=1, a=2, b=3)
+        r3, c3 = ctx.sw_extend_batch(B.make_params(**pk), *flat)
+        ro3, co3 = O.extend_batch(O.make_params(**pk), *flat)
+        assert_same(ro3, r3, "raw mode, other scoring")
+        custom = B.bwa_fill_scmat(1, 4).copy(); custom[1] = -2; custom[5] = -2                     # not +a/-b: matrix-lookup kernel, no rerun
+        r4, _ = ctx.sw_extend_batch(B.make_params(mat=custom), *flat)
+        ro4, _ = O.extend_batch(O.make_params(mat=custom), *flat)
+        assert_same(ro4, r4, "raw mode, custom matrix")
+        bad = t["tbuf"][int(t["toff"][12345]) + 3]
+        t["tbuf"][int(t["toff"][12345]) + 3] = 9
+        with pytest.raises(B.BswError) as e:
+            ctx.sw_extend_batch(p, *flat)
+        t["tbuf"][int(t["toff"][12345]) + 3] = bad
+        assert e.value.code == B.BSW_EINVAL and "task 12345" in str(e.value)
+        ctx.set_option("raw_inputs", 0)
+        ctx.reset_stats()
+        r5, _ = ctx.sw_extend_batch(p, *flat)
+        assert ctx.stats()["h2d_bytes"] < st["h2d_bytes"]                     # staged again: 4 bit per base
+        ctx.set_option("raw_inputs", 1)
+        assert_same(ro, r5, "staged path on registered buffers")
+        # a mixed batch with long tasks: those chunks are staged, the rest stays raw
+        lt = B.synth_tasks("cfg4_long", 6, seed=42)
+        qbuf = np.concatenate([t["qbuf"][:t["qoff"][2000]], lt["qbuf"]]); tbuf = np.concatenate([t["tbuf"][:t["toff"][2000]], lt["tbuf"]])
+        qoff = np.concatenate([t["qoff"][:2001], lt["qoff"][1:] + t["qoff"][2000]]); toff = np.concatenate([t["toff"][:2001], lt["toff"][1:] + t["toff"][2000]])
+        h0 = np.concatenate([t["h0"][:2000], lt["h0"]]); w = np.concatenate([t["w"][:2000], lt["w"]])
+        ctx.register_host(qbuf); ctx.register_host(tbuf)
+        try:
+            r6, c6 = ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, h0, w)
+        finally:
+            ctx.unregister_host(qbuf); ctx.unregister_host(tbuf)
+        ro6, co6 = O.extend_batch(po, qbuf, qoff, tbuf, toff, h0, w)
+        assert_same(ro6, r6, "raw + long tasks")
+    finally:
+        ctx.unregister_host(t["qbuf"]); ctx.unregister_host(t["tbuf"])
+
+
 def test_level3_wire_format(B, O, ctx):
     """TBB image in, RBB image out (the FPGA has no z-drop and a fixed +1/-4/-1 matrix: compare with zdrop=0)."""
     t = B.synth_tasks("cfg1_101bp", 1600, seed=30)

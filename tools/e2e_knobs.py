@@ -11,6 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     t = B.synth_tasks(sys.argv[2], n)
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     out = np.zeros(n, dtype=B.RESULT_DTYPE)
+    if os.environ.get("REG"): ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"])      # raw mode: no host staging
     tag = " ".join("%s=%s" % (k, os.environ.get(k)) for k in ("CUDA_DEVICE_MAX_CONNECTIONS", "BSW_BUCKET_PCT", "BSW_SIDE_STREAMS"))
     for slots in (2, 3):
         for chunk in (8192, 12288, 16384, 24576):
