@@ -106,7 +106,8 @@ struct bsw_ctx {
     SchedOptions opt;
     size_t chunk_tasks = 16384;
     int slots_per_worker = 2;
-    bool raw_inputs = true;        // flat batches whose base buffers are registered (bsw_host_register) skip the host packer
+    int raw_inputs = 2;            // flat batches whose base buffers are registered (bsw_host_register) skip the host packer:
+                                   // 0 never, 1 always, 2 auto (when there are at most 10 host threads per GPU)
     std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
@@ -504,7 +505,14 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
 
     // chunk size: chunk_tasks for short reads, fewer tasks per chunk when they are long (about 6 MB of bases per chunk),
     // so that a batch of long tasks still spreads over all the host workers
-    size_t chunk = std::max<size_t>(32, ctx->chunk_tasks);
+    // Raw mode (bases in registered host memory, no staging pass) trades host work for PCIe bytes: measured on
+    // 1 M x 150 bp it wins below ~10 host threads per GPU (4 threads: 7.5 vs 10.6 ms, 8: 6.6 vs 7.1) and loses above
+    // (16 threads: 6.5 vs 5.8 ms), so "auto" takes it only when the host is the scarce side.  Its copies are per
+    // buffer, so it runs on chunks twice the usual size.
+    const size_t ndev = ctx->devs.size();
+    const bool allow_raw = src.raw && rerun_n_out != nullptr &&
+                           (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (size_t)opt.host_threads <= 10 * ndev));
+    size_t chunk = std::max<size_t>(32, allow_raw ? 2 * ctx->chunk_tasks : ctx->chunk_tasks);
     {
         const size_t probe = std::min<size_t>(n, 512);
         std::vector<ExtTask> pv(probe);
@@ -519,7 +527,6 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         chunk = std::min(chunk, std::max<size_t>(2048, (per_worker + 31) & ~(size_t)31));
     }
     const size_t nchunks = (n + chunk - 1) / chunk;
-    const size_t ndev = ctx->devs.size();
     size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
     if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
     if (nworkers < 1) nworkers = 1;
@@ -540,7 +547,6 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     std::mutex stat_mu;
     LocalStats total;
     std::vector<size_t> overflow_all, rerun_all;
-    const bool allow_raw = src.raw && rerun_n_out != nullptr && ctx->raw_inputs;
 
     auto worker_main = [&](size_t k) {
         Worker& W = *ctx->workers[k];
@@ -777,7 +783,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     const std::string k(key);
     if (k == "variant") { if (value != 1 && value != 2) return BSW_EINVAL; ctx->opt.variant = (int)value; }
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
-    else if (k == "raw_inputs") { ctx->raw_inputs = value != 0; }
+    else if (k == "raw_inputs") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->raw_inputs = (int)value; }
     else if (k == "slots") { if (value < 1 || value > 16) return BSW_EINVAL; ctx->slots_per_worker = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }

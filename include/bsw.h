@@ -54,8 +54,8 @@ void bsw_destroy(bsw_ctx *ctx);
 const char *bsw_last_error(const bsw_ctx *ctx);          /* thread-unsafe convenience: last error text of this ctx */
 const char *bsw_version(void);
 /* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity, default 16384);
- * "slots" N (chunks one host worker keeps in flight, default 2); "raw_inputs" {0,1} use the no-staging path for
- * registered buffers (default 1);
+ * "slots" N (chunks one host worker keeps in flight, default 2); "raw_inputs" {0 never, 1 always, 2 auto} use the
+ * no-staging path for registered buffers (default 2: when the context has at most 10 host threads per GPU);
  * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
  * "k2_warps" {1,4} warps per K2 task; "fused_l2" {0,1} level 2 as one fused kernel (default 1);
  * experimental kernels, off by default because they measured slower: "k1_pair", "ring", "k2_sub";

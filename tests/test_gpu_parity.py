@@ -219,6 +219,7 @@ def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     ro, co = O.extend_batch(po, *flat)
     ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"])
+    ctx.set_option("raw_inputs", 1)                  # default is "auto": raw only when host threads are scarce
     try:
         ctx.reset_stats()
         r, c = ctx.sw_extend_batch(p, *flat)
@@ -265,7 +266,17 @@ def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
             ctx.unregister_host(qbuf); ctx.unregister_host(tbuf)
         ro6, co6 = O.extend_batch(po, qbuf, qoff, tbuf, toff, h0, w)
         assert_same(ro6, r6, "raw + long tasks")
+        # auto: with a couple of host threads the raw path is taken, with many the staged one
+        ctx.set_option("raw_inputs", 2)
+        for threads, expect_raw in ((2, True), (16, False)):
+            ctx.set_option("host_threads", threads)
+            ctx.reset_stats()
+            r7, _ = ctx.sw_extend_batch(p, *flat)
+            assert_same(ro, r7, f"auto, {threads} host threads")
+            assert (ctx.stats()["h2d_bytes"] > int(t["qoff"][-1] + t["toff"][-1])) == expect_raw
+        ctx.set_option("host_threads", 0)
     finally:
+        ctx.set_option("raw_inputs", 2); ctx.set_option("host_threads", 0)
         ctx.unregister_host(t["qbuf"]); ctx.unregister_host(t["tbuf"])
 
 
