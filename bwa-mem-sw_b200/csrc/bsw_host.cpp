@@ -999,6 +999,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     };
     auto submit = [&](Slot& sl, size_t first, size_t range) -> int {
         int r = 0;
+        sl.raw_mode = false;                     // the slot may have carried a raw-mode level-1 chunk before
         sl.seed_idx.clear();
         {
             std::vector<size_t> left;

@@ -266,6 +266,11 @@ def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
             ctx.unregister_host(qbuf); ctx.unregister_host(tbuf)
         ro6, co6 = O.extend_batch(po, qbuf, qoff, tbuf, toff, h0, w)
         assert_same(ro6, r6, "raw + long tasks")
+        # level 2 right after raw-mode level-1 chunks reuses the same stream slots (regression: stale raw flag)
+        seeds = seeds_from_flat(t, 3000, unset_score_every=3)
+        P2 = B.make_params2(p, w=100, pen_clip5=5, pen_clip3=5)
+        want2, _ = oracle_chain2aln(O, B, P2, seeds)
+        assert_same(want2, ctx.proc_element_batch(P2, seeds), "level 2 after raw mode")
         # auto: with a couple of host threads the raw path is taken, with many the staged one
         ctx.set_option("raw_inputs", 2)
         for threads, expect_raw in ((2, True), (16, False)):

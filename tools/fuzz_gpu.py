@@ -1,6 +1,6 @@
 """Randomised parity campaign on the GPU: medium-length adversarial tasks (rows long enough for the 16-cell path, ties,
 indels, N, tiny h0 / w), random scoring, V1 and V2, level 1 through the default kernel choice and K2, level 2 fused.
-Usage: python tools/fuzz_gpu.py [iterations] [first_seed]"""
+Usage: [RAW=1] python tools/fuzz_gpu.py [iterations] [first_seed]   (RAW=1: every other iteration uses registered buffers)"""
 import sys, os, time
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -28,6 +28,9 @@ for it in range(iters):
                                          b=int(rng.integers(1, 7)), end_bonus=int(rng.integers(0, 10)))
     p, po = B.make_params(**pk), O.make_params(**pk)
     flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    raw = bool(os.environ.get("RAW")) and it % 2 == 1          # every other iteration through the raw input mode
+    if raw:
+        ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"]); ctx.set_option("raw_inputs", 1)
     for variant in (1, 2):
         ro, co = O.extend_batch(po, *flat, variant=variant)
         for opts in (dict(), dict(force_kernel=2)) if variant == 1 else (dict(),):
@@ -39,6 +42,8 @@ for it in range(iters):
                 bad = np.nonzero((ro != rg) | (co.astype(np.int64) != cg.astype(np.int64)))[0]
                 print("MISMATCH it=%d variant=%d opts=%s pk=%s first task %d: oracle %s gpu %s" % (it, variant, opts, pk, bad[0], ro[bad[0]], rg[bad[0]]), flush=True)
                 fails += 1
+    if raw:
+        ctx.unregister_host(t["qbuf"]); ctx.unregister_host(t["tbuf"]); ctx.set_option("raw_inputs", 2)
     # level 2 on flank pairs
     seeds = []
     sl = lambda a, off, i: a[off[i]:off[i + 1]]
