@@ -768,6 +768,7 @@ void bsw_destroy(bsw_ctx* ctx)
         slot_free(D.aux);
     }
     for (const auto& r : ctx->host_regs) cudaHostUnregister(const_cast<unsigned char*>(r.first));
+    if (ctx->trace_ref) cudaEventDestroy(ctx->trace_ref);
     cudaSetDevice(prev);
     delete ctx;
 }
