@@ -453,6 +453,7 @@ def emu_lib() -> C.CDLL:
         vp = C.c_void_p
         E.bsw_emu_extend_batch_flat.argtypes = [C.POINTER(Params), C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp]
         E.bsw_emu_chain2aln.argtypes = [C.POINTER(Params2), C.c_int, vp, C.c_size_t, vp]
+        E.bsw_emu_chain2aln_wire.argtypes = [C.POINTER(Params2), C.c_int, vp, C.c_size_t, vp, vp]
         _emu = E
     return _emu
 
@@ -470,11 +471,16 @@ def emu_extend_batch(params: Params, qbuf, qoff, tbuf, toff, h0, w, variant: int
     return out, cells, info
 
 
-def emu_chain2aln(params2: Params2, seeds, variant: int = 1):
-    """TEST ONLY: level 2 through the host scheduler + the K3 lane function compiled for the CPU."""
+def emu_chain2aln(params2: Params2, seeds, variant: int = 1, wire_gaps=None):
+    """TEST ONLY: level 2 through the host scheduler + the K3 lane function compiled for the CPU.
+    wire_gaps: (n, 4) max_ins/max_del per side as a TBB carries them = the mode bsw_fpga_batch runs in."""
     tasks, keep = make_seed_tasks(seeds)
     out = np.zeros(len(seeds), dtype=ALN_DTYPE)
-    rc = emu_lib().bsw_emu_chain2aln(C.byref(params2), variant, tasks, len(seeds), out.ctypes.data)
+    if wire_gaps is not None:
+        g = np.ascontiguousarray(wire_gaps, dtype=np.int32).reshape(len(seeds), 4)
+        rc = emu_lib().bsw_emu_chain2aln_wire(C.byref(params2), variant, tasks, len(seeds), g.ctypes.data, out.ctypes.data)
+    else:
+        rc = emu_lib().bsw_emu_chain2aln(C.byref(params2), variant, tasks, len(seeds), out.ctypes.data)
     del keep
     if rc != BSW_OK:
         raise BswError(rc, "emulation (level 2)")

@@ -911,6 +911,12 @@ static int chain2aln_host(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_tas
             for (size_t e = 0; e < who.size(); ++e) {
                 const size_t i = who[e];
                 prev[i] = a_score[i];                                     // sx:1822,1859
+                if (clamps && k > 0) {                                    // wire tasks: the FPGA carries the first try's maxima
+                    const bsw_result first = cur[i];                      // (k3_rtl_carry, bsw_k3_core.cuh)
+                    bsw_result& second = res[e];
+                    if (!(second.score > first.score)) { second.score = first.score; second.qle = first.qle; second.tle = first.tle; }
+                    if (second.gscore < first.gscore) { second.gscore = first.gscore; second.gtle = first.gtle; }
+                }
                 a_score[i] = res[e].score; cur[i] = res[e]; st[i].aw[side] = aw;
                 if (!(a_score[i] == prev[i] || res[e].max_off < (aw >> 1) + (aw >> 2))) again.push_back(i);   // sx:1824-1825,1969-1970,1837
             }

@@ -28,6 +28,18 @@ BSW_HD int k3_clamp(const DevParams& P, int qlen, int aw, int end_bonus, int max
 
 constexpr int K3_MAX_BAND_TRY = 2;
 
+// The RTL initialises max / max_i / max_j / max_ie / gscore once per sw_extend invocation, BEFORE its band-try loop
+// (sw_pe_array_sw_extend.v:885-890,913-930,957-959), where ksw_extend2 starts every call afresh: the FPGA's second try
+// continues from the first try's maxima (seen on ~2 % of the second tries of the translated
+// RTL, tests/golden/rtl_*.npz).  Both update rules are monotone -- a row replaces (max, max_i, max_j) only when it beats
+// the running max (sx:1959), and (gscore, max_ie) when it is not below the running gscore (sx:1941) -- so the carried
+// second try equals this merge of the two stand-alone results.  Applied to wire tasks only: everything else follows BWA.
+BSW_HD void k3_rtl_carry(const SlotResult& first, SlotResult& second)
+{
+    if (!(second.score > first.score)) { second.score = first.score; second.qle = first.qle; second.tle = first.tle; }
+    if (second.gscore < first.gscore) { second.gscore = first.gscore; second.gtle = first.gtle; }
+}
+
 // spL/spR: the left / right flank (qlen == 0: no extension on that side, pe:1670).  The left flanks arrive reversed.
 template <int VARIANT, int GENERIC, int SYM>
 BSW_HD void k3_seed(const DevParams& P, int w, int pen_clip5, int pen_clip3, const SlotParam& spL, const SlotParam& spR,
@@ -51,9 +63,11 @@ BSW_HD void k3_seed(const DevParams& P, int w, int pen_clip5, int pen_clip3, con
             const int prev = a_score;                                            // sx:1822,1859
             aw = w << k;                                                         // sx:1765
             const int weff = k3_clamp(P, sp.qlen, aw, pen_clip, sd.max_ins[side], sd.max_del[side]);
+            const SlotResult r0 = r;
             k1_task<VARIANT, GENERIC, SYM>(P, sp.qlen, sp.tlen, h0, weff, side ? nqwR : nqwL, eh, side ? qsR : qsL,
                                            side ? tgR : tgL, r, k == 0);
             cells += (uint32_t)r.cells;
+            if (k > 0 && sd.max_ins[side] >= 0) k3_rtl_carry(r0, r);             // wire tasks only (bsw_fpga_batch)
             a_score = r.score;
             if (a_score == prev || r.max_off < (aw >> 1) + (aw >> 2)) break;     // sx:1824-1825,1969-1970,1837
         }

@@ -270,7 +270,18 @@ void run_seed_pair(const DevParams& dp, int w, int pc5, int pc3, const TileHdr& 
 }
 }  // namespace
 
+// gaps4 (may be null): per seed {max_ins_left, max_del_left, max_ins_right, max_del_right} as a TBB carries them --
+// the wire mode of bsw_fpga_batch (host-supplied band clamp, the FPGA's carried second band try).
+extern "C" int bsw_emu_chain2aln_wire(const bsw_params2* P2, int variant, const bsw_seed_task* tasks, size_t n,
+                                      const int32_t* gaps4, bsw_aln_record* out);
+
 extern "C" int bsw_emu_chain2aln(const bsw_params2* P2, int variant, const bsw_seed_task* tasks, size_t n, bsw_aln_record* out)
+{
+    return bsw_emu_chain2aln_wire(P2, variant, tasks, n, nullptr, out);
+}
+
+extern "C" int bsw_emu_chain2aln_wire(const bsw_params2* P2, int variant, const bsw_seed_task* tasks, size_t n,
+                                      const int32_t* gaps4, bsw_aln_record* out)
 {
     const bsw_params* params = &P2->p;
     if (params->e_ins < 1 || params->e_del < 1 || params->o_ins < 0 || params->o_del < 0) return BSW_EINVAL;
@@ -317,6 +328,10 @@ extern "C" int bsw_emu_chain2aln(const bsw_params2* P2, int variant, const bsw_s
         if (si < 0) { sp[q] = SeedParam{ 0, 0, -1, 0, { -1, -1 }, { -1, -1 } }; continue; }
         const bsw_seed_task& s = tasks[si];
         sp[q] = SeedParam{ s.init_score, s.qbeg, s.h0 > 0 ? s.h0 : 0, s.id, { -1, -1 }, { -1, -1 } };
+        if (gaps4) {
+            sp[q].max_ins[0] = gaps4[4 * si + 0]; sp[q].max_del[0] = gaps4[4 * si + 1];
+            sp[q].max_ins[1] = gaps4[4 * si + 2]; sp[q].max_del[1] = gaps4[4 * si + 3];
+        }
     }
     std::vector<SeedRecord> rec(P.lane_seed.size());
     for (const Launch& L : P.launches) {

@@ -63,6 +63,12 @@ def lib():
         _lib.bswref_chain2aln_batch.restype = None
         _lib.bswref_chain2aln_batch.argtypes = [C.POINTER(Params2), C.c_int, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+        _lib.bswref_sw_extend_rtl.restype = None
+        _lib.bswref_sw_extend_rtl.argtypes = [C.POINTER(Params), C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + \
+                                             [C.c_void_p, C.POINTER(C.c_int64)]
+        _lib.bswref_chain2aln_rtl.restype = None
+        _lib.bswref_chain2aln_rtl.argtypes = [C.POINTER(Params2), C.POINTER(SeedTask), C.c_void_p, C.c_void_p,
+                                              C.POINTER(C.c_int64)]
         _lib.bswref_max_threads.restype = C.c_int
         _lib.bswref_clamp_w.restype = C.c_int
         _lib.bswref_clamp_w.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int]
@@ -105,6 +111,31 @@ def extend_one(params: Params, query, target, h0: int, w: int, variant: int = 1)
     return out[0], int(cells.value)
 
 
+def sw_extend_rtl(params: Params, query, target, h0: int, w: int, reg_score: int, max_ins: int, max_del: int):
+    """One whole RTL sw_extend invocation in int32: host-supplied band clamp, two band tries with the maxima carried
+    from try to try, no z-drop.  Returns (int32[7] = score, aw, qle, tle, gtle, gscore, max_off; cells)."""
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    out = np.zeros(7, dtype=np.int32)
+    cells = C.c_int64(0)
+    lib().bswref_sw_extend_rtl(C.byref(params), len(q), q.ctypes.data, len(t), t.ctypes.data, int(w), int(h0),
+                               int(reg_score), int(max_ins), int(max_del), out.ctypes.data, C.byref(cells))
+    return out, int(cells.value)
+
+
+def rtl_envelope(qlen, tlen, h0, w, o_del=6, e_del=1, o_ins=6, e_ins=1) -> bool:
+    """True when the FPGA's 8-bit datapath computes one sw_extend call without wrapping, i.e. when the RTL and int32
+    ksw_extend2 must agree (checked against the translated RTL on tests/golden/rtl_sw_extend*.npz:
+    no task inside this envelope differs, tasks outside it do).
+      scores      h0 + qlen*max(mat) <= 127: H/E/F/max are 8 bit, compared signed (sw_pe_array_sw_extend.v:155-159,1943-1945)
+      columns     qlen <= 127: mj is sign-extended in max_off and in the narrowing compares (sx:1654,1336,1547)
+      first col.  h0 - o_del - e_del*tlen >= -128: h1 is a running 8-bit subtraction clipped by its sign bit (sx:1795,890-907)
+      first row   h0 - o_ins - e_ins*qlen >= -128: same for the row-0 generator (sx:1072,1975)
+      band        w <= 63: w << 1 is a signed 8-bit value in the second band try (sx:770,775)"""
+    return bool(qlen <= 127 and h0 + qlen <= 127 and h0 - o_del - e_del * tlen >= -128
+                and h0 - o_ins - e_ins * qlen >= -128 and 0 < w <= 63 and 0 < h0 and 0 < qlen and 0 < tlen <= 2047)
+
+
 def extend_batch(params: Params, qbuf, qoff, tbuf, toff, h0, w, variant: int = 1, nthreads: int = 0):
     """Level-1 oracle over a flat batch.  Returns (results[RESULT_DTYPE], cells_per_task[int64])."""
     qbuf = np.ascontiguousarray(qbuf, dtype=np.uint8)
@@ -130,4 +161,17 @@ def chain2aln_batch(params2: Params2, seed_tasks, variant: int = 1, nthreads: in
     cells = C.c_int64(0)
     lib().bswref_chain2aln_batch(C.byref(params2), variant, n, C.addressof(seed_tasks) if n else None,
                                  out.ctypes.data, C.byref(cells), int(nthreads))
+    return out, int(cells.value)
+
+
+def chain2aln_rtl(params2: Params2, seed_tasks, gaps):
+    """Level 2 exactly as the RTL sequences it: gaps[i] = (max_ins_left, max_del_left, max_ins_right, max_del_right)
+    from the TBB (host-supplied band clamp), each side one whole sw_extend invocation (sw_extend_rtl)."""
+    n = len(seed_tasks)
+    out = np.zeros(n, dtype=ALN_DTYPE)
+    gaps = np.ascontiguousarray(gaps, dtype=np.int32).reshape(n, 4)
+    cells = C.c_int64(0)
+    for i in range(n):
+        lib().bswref_chain2aln_rtl(C.byref(params2), C.byref(seed_tasks[i]), gaps[i].ctypes.data,
+                                   out[i:i + 1].ctypes.data, C.byref(cells))
     return out, int(cells.value)

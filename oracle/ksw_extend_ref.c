@@ -63,9 +63,27 @@ int bswref_clamp_w(const bswref_params *p, int qlen, int w, int end_bonus)
  * (the PE never calls sw_extend with qlen==0: pe:1670).
  * `scratch` must hold (qlen+1) eh_t.  Returns score; fills *out; adds executed cells to *cells.
  */
+/* `carry` (normally NULL): the running maxima of a previous band try.  ksw_extend2 re-initialises them on every call;
+ * the RTL initialises max / max_i / max_j / max_ie / gscore / max_off once per sw_extend invocation, i.e. BEFORE the
+ * band-try loop (sx:885-890,913-930,957-959,1003-1031), so its second try starts from the first try's values
+ * (SURVEY appendix C row 5).  Only bswref_sw_extend_rtl() passes a carry; it exists to compare against the translated
+ * RTL (oracle/_ref) on tasks where the second try runs. */
+typedef struct { int32_t valid, max, max_i, max_j, max_ie, gscore, max_off; } bswref_carry;
+
+static int bswref_extend_core_x(const bswref_params *p, int variant, int qlen, const uint8_t *query,
+                       int tlen, const uint8_t *target, int w, int h0,
+                       bswref_result *out, int64_t *cells, eh_t *eh, bswref_carry *carry, int clamp_w);
+
 int bswref_extend_core(const bswref_params *p, int variant, int qlen, const uint8_t *query,
                        int tlen, const uint8_t *target, int w, int h0,
                        bswref_result *out, int64_t *cells, eh_t *eh)
+{
+    return bswref_extend_core_x(p, variant, qlen, query, tlen, target, w, h0, out, cells, eh, NULL, 1);
+}
+
+static int bswref_extend_core_x(const bswref_params *p, int variant, int qlen, const uint8_t *query,
+                       int tlen, const uint8_t *target, int w, int h0,
+                       bswref_result *out, int64_t *cells, eh_t *eh, bswref_carry *carry, int clamp_w)
 {
     const int o_del = p->o_del, e_del = p->e_del, o_ins = p->o_ins, e_ins = p->e_ins;
     const int oe_del = o_del + e_del;            /* sx:1860 */
@@ -74,7 +92,7 @@ int bswref_extend_core(const bswref_params *p, int variant, int qlen, const uint
     int i, j, beg, end, max, max_i, max_j, max_ie, gscore, max_off;
     int64_t ncell = 0;
 
-    w = bswref_clamp_w(p, qlen, w, p->end_bonus);
+    if (clamp_w) w = bswref_clamp_w(p, qlen, w, p->end_bonus);
 
     /* first row: eh[j].h = H(-1, j-1), all e = 0  (sx:1818; 1979,1957,1974; 1975-1978,1821) */
     memset(eh, 0, sizeof(eh_t) * (size_t)(qlen + 1));
@@ -83,6 +101,10 @@ int bswref_extend_core(const bswref_params *p, int variant, int qlen, const uint
     for (j = 2; j <= qlen && eh[j - 1].h > e_ins; ++j) eh[j].h = eh[j - 1].h - e_ins;
 
     max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;   /* sx:889,1009,919,1019,1029,929 */
+    if (carry && carry->valid) {                                            /* RTL second band try: see bswref_carry */
+        max = carry->max; max_i = carry->max_i; max_j = carry->max_j;
+        max_ie = carry->max_ie; gscore = carry->gscore; max_off = carry->max_off;
+    }
     beg = 0; end = qlen;                                                    /* sx:769,779 */
     for (i = 0; i < tlen; ++i) {                                            /* sx:1891 */
         int f = 0, h1, m = 0, mj = -1;                                      /* sx:789,879,909 */
@@ -153,7 +175,39 @@ int bswref_extend_core(const bswref_params *p, int variant, int qlen, const uint
     out->gscore = gscore;                                                   /* sx:1792 */
     out->max_off = max_off;                                                 /* sx:1815 */
     if (cells) *cells += ncell;
+    if (carry) {
+        carry->valid = 1; carry->max = max; carry->max_i = max_i; carry->max_j = max_j;
+        carry->max_ie = max_ie; carry->gscore = gscore; carry->max_off = max_off;
+    }
     return max;
+}
+
+/* One invocation of the RTL's sw_extend as a whole (sx:1639-1705): band clamp from the host-supplied max_ins / max_del
+ * (sx:1763-1765,1881,1890), up to two band tries with `prev` seeded from regScore (sx:1069,1822,1859) and the maxima
+ * carried from try to try, no z-drop.  out7 = ap_return_0..6 = score, aw, qle, tle, gtle, gscore, max_off
+ * (sx:117-123,1315-1375).  int32 arithmetic: equal to the RTL wherever the RTL's 8-bit datapath does not wrap. */
+void bswref_sw_extend_rtl(const bswref_params *p, int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                          int w, int h0, int reg_score, int max_ins, int max_del, int32_t *out7, int64_t *cells)
+{
+    eh_t *eh = (eh_t *)malloc(sizeof(eh_t) * (size_t)(qlen + 1));
+    bswref_params pp = *p;
+    bswref_carry carry;
+    bswref_result res;
+    int k, aw = w, score = reg_score, prev;
+    memset(&carry, 0, sizeof carry);
+    memset(&res, 0, sizeof res);
+    pp.zdrop = 0;
+    for (k = 0; k < 2; ++k) {                                               /* sx:1963,1878 */
+        int wk;
+        prev = score;                                                       /* sx:1822,1859 */
+        aw = w << k;                                                        /* sx:1765 */
+        wk = imin(aw, imin(max_ins, max_del));                              /* sx:1764,1881 ; 1763,1890 */
+        score = bswref_extend_core_x(&pp, 1, qlen, query, tlen, target, wk, h0, &res, cells, eh, &carry, 0);
+        if (score == prev || res.max_off < (aw >> 1) + (aw >> 2)) break;    /* sx:1824-1825,1969-1970,1837 */
+    }
+    out7[0] = score; out7[1] = aw; out7[2] = res.qle; out7[3] = res.tle;
+    out7[4] = res.gtle; out7[5] = res.gscore; out7[6] = res.max_off;
+    free(eh);
 }
 
 int bswref_extend(const bswref_params *p, int variant, int qlen, const uint8_t *query,
@@ -255,8 +309,12 @@ typedef struct { uint32_t id; int32_t qb, qe, rb, re, score, truesc, w; } bswref
 
 #define BSWREF_MAX_BAND_TRY 2
 
-void bswref_chain2aln(const bswref_params2 *P, int variant, const bswref_seed_task *s,
-                      bswref_aln_record *r, int64_t *cells)
+/* rtl_gaps == NULL: BWA's mem_chain2aln loop (every band try is a fresh ksw_extend2 call, clamp from the formula).
+ * rtl_gaps != NULL: {max_ins_left, max_del_left, max_ins_right, max_del_right} as the TBB carries them (pe:924-934);
+ * each side is then ONE invocation of the RTL's sw_extend (bswref_sw_extend_rtl: maxima carried across the two tries,
+ * no z-drop) -- the mode compared against the translated RTL in oracle/_ref. */
+static void chain2aln_impl(const bswref_params2 *P, int variant, const bswref_seed_task *s,
+                           bswref_aln_record *r, int64_t *cells, const int32_t *rtl_gaps)
 {
     /* initial state: pe:471-475,581-583,605-607,649-651,673-675,707-709,717-719,757-759,783-797 */
     int qb = 0, rb = 0, qe = s->qlen[1], re = 0, score = 0;
@@ -274,6 +332,12 @@ void bswref_chain2aln(const bswref_params2 *P, int variant, const bswref_seed_ta
         h0 = side ? sc0 : s->h0;                                            /* pe:1671,1652 */
         pp.end_bonus = pen_clip;                                            /* BWA passes pen_clip5/3 as ksw_extend2's end_bonus */
         a_score = sc0;
+        if (rtl_gaps) {
+            int32_t o7[7];
+            bswref_sw_extend_rtl(&pp, ql, q, tl, t, P->w, h0, sc0, rtl_gaps[2 * side], rtl_gaps[2 * side + 1], o7, cells);
+            a_score = o7[0]; aw[side] = o7[1];
+            res.score = o7[0]; res.qle = o7[2]; res.tle = o7[3]; res.gtle = o7[4]; res.gscore = o7[5]; res.max_off = o7[6];
+        } else
         for (k = 0; k < BSWREF_MAX_BAND_TRY; ++k) {                         /* sx:1963,1878 */
             prev = a_score;                                                 /* sx:1822,1859 */
             aw[side] = P->w << k;                                           /* sx:1765 */
@@ -293,6 +357,19 @@ void bswref_chain2aln(const bswref_params2 *P, int variant, const bswref_seed_ta
     r->qb = qb; r->qe = qe; r->rb = rb; r->re = re;
     r->score = score; r->truesc = truesc;
     r->w = aw[0] > aw[1] ? aw[0] : aw[1];                                   /* pe:1669,1684 */
+}
+
+void bswref_chain2aln(const bswref_params2 *P, int variant, const bswref_seed_task *s,
+                      bswref_aln_record *r, int64_t *cells)
+{
+    chain2aln_impl(P, variant, s, r, cells, NULL);
+}
+
+/* One FPGA processing element's task exactly as the RTL sequences it (see chain2aln_impl). */
+void bswref_chain2aln_rtl(const bswref_params2 *P, const bswref_seed_task *s, const int32_t *gaps4,
+                          bswref_aln_record *r, int64_t *cells)
+{
+    chain2aln_impl(P, 1, s, r, cells, gaps4);
 }
 
 typedef struct {

@@ -80,3 +80,22 @@ def random_small_tasks(rng, n, qmax=60, tmax=90):
         w.append(int(rng.choice([0, 1, 2, 3, 5, 10, 30, 100])))
     qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
     return dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
+
+
+def parse_tbb(tbb):
+    """Field map: proc_element.v:815-820,915-918 (header), :880-892,871-874,826-828,924-934,807 (param words),
+    task_parse.v:1924-1936 (data offsets), proc_element.v:1638,1677 (MS nibble first)."""
+    hdr = dict(o_del=tbb[0] & 0xff, e_del=(tbb[0] >> 8) & 0xff, o_ins=(tbb[0] >> 16) & 0xff, e_ins=tbb[0] >> 24,
+               pen_clip5=tbb[1] & 0xff, pen_clip3=(tbb[1] >> 8) & 0xff, w=(tbb[1] >> 16) & 0xff, n=int(tbb[2]))
+    n = hdr["n"]
+    off0 = int(tbb[8 + 2])
+    tasks = []
+    for i in range(n):
+        pw = [int(x) for x in tbb[8 + 8 * i: 16 + 8 * i]]
+        ql, tl = [pw[0] & 0xff, pw[1] & 0xff], [(pw[0] >> 16) & 0x7ff, (pw[1] >> 16) & 0x7ff]
+        nb = ql[0] + ql[1] + tl[0] + tl[1]
+        base = 8 + 8 * n + (pw[2] - off0)
+        bases = [(int(tbb[base + (k >> 3)]) >> (28 - 4 * (k & 7))) & 15 for k in range(nb)]
+        tasks.append(dict(qlen=ql, tlen=tl, init_score=pw[3] & 0xffff, qbeg=pw[3] >> 16, h0=pw[4] & 0xff,
+                          max_ins=[pw[5] & 0xffff, pw[6] & 0xffff], max_del=[pw[5] >> 16, pw[6] >> 16], id=pw[7], bases=bases))
+    return hdr, tasks
