@@ -216,7 +216,7 @@ def main():
     out_buf = np.zeros(n, dtype=B.RESULT_DTYPE)                     # caller-owned result array, as a C caller would hold
     # the caller's base buffers are page-locked in place, as a host that reuses its batch buffers would hold them; the
     # library then chooses per call between staging with host threads and copying the bases in place ("raw_inputs" auto)
-    ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"])
+    ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"]); ctx.register_host(out_buf)
     for _ in range(max(args.warmup, 3)):
         ctx.sw_extend_batch(p, *flat, want_cells=False, out=out_buf)
     ctx.reset_stats()
@@ -268,7 +268,7 @@ def main():
                     "tasks_per_s": n * world * steps / e2e_s, "ms_per_step": e2e_s / steps * 1e3,
                     "h2d_bytes_per_step": int(st["h2d_bytes"] // steps), "d2h_bytes_per_step": int(st["d2h_bytes"] // steps),
                     "host_pack_ms_per_step": st["pack_ms"] / steps, "host_threads": host_threads,
-                    "inputs": "numpy arrays registered with bsw_host_register (page-locked in place); raw_inputs=auto"},
+                    "inputs": "numpy base and result arrays registered with bsw_host_register (page-locked in place); raw_inputs=auto, device_plan=1"},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tops/s", "frac": achieved / int_peak,

@@ -243,9 +243,10 @@ class Context:
 
     # ---- level 1: sw_extend ----
     def register_host(self, arr: np.ndarray) -> None:
-        """Page-lock a long-lived uint8 base buffer in place (bsw_host_register): flat batches whose bases live in
-        registered buffers skip the host staging pass.  Keep the array alive until unregister_host / close."""
-        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        """Page-lock a long-lived buffer in place (bsw_host_register): flat batches whose bases live in registered uint8
+        buffers skip the host staging pass, and a registered result array receives its records straight from the device.
+        Keep the array alive until unregister_host / close."""
+        assert arr.flags.c_contiguous
         self._check(lib().bsw_host_register(self.handle, arr.ctypes.data, arr.nbytes))
 
     def unregister_host(self, arr: np.ndarray) -> None:

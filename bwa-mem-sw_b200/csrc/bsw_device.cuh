@@ -65,6 +65,30 @@ struct GatherArgs {
     const uint8_t*   raw_q;
     const uint8_t*   raw_t;
     uint32_t*        slot_flags;   // per slot: SLOT_HAS_N | SLOT_BAD_CODE
+    TileHdr*         dp_tiles;     // device-planned chunk: the gather takes the tiles' word counts (warp max) into the headers
+};
+
+// Device-side scheduler (bsw_plan.cu): the chunk's tasks in input order in, tile / slot arrays out.
+struct DpArgs {
+    const SlotParam* task_param;   // [count] {qlen, tlen, h0, w} in task order
+    const SlotSrc*   task_src;     // [count] where each task's sequences sit in the source arena (or raw byte offsets)
+    const uint8_t*   task_cls;     // [count] bit0 = needs matrix-lookup scoring; null: every task has class const_cls
+    uint32_t const_cls;
+    uint32_t count;
+    uint32_t class_count[2];       // tasks per matrix class (host-known: the packer classifies)
+    uint32_t class_pos0[2];        // first sorted position of the class (0, class_count[0])
+    uint32_t class_slot0[2];       // first slot of the class (a multiple of 32)
+    uint32_t class_tile0[2];       // first tile of the class
+    uint32_t ntiles;
+    uint32_t nmajor;               // non-empty (class, qlen/16) buckets, in sorted order (class ascending, qlen descending)
+    uint32_t major_start[192];     // first sorted position of each
+    uint8_t  major_of[256];        // (class << 7 | qlen/16) -> index of its bucket
+    uint32_t* bins;                // [nmajor * 4096] counters, then running positions
+    uint32_t* task_bin;            // [count] bin of every task
+    TileHdr*   tiles;              // [ntiles] qoff16 / toff16 / slot0 pre-filled by the host; nqw_ntw written by the K0 gather
+    SlotParam* slots;              // [nslots]
+    SlotSrc*   slot_src;           // [nslots]
+    uint32_t*  out_index;          // [nslots] task index of the slot, 0xffffffff = padding lane
 };
 
 // Per-seed scalars of the fused level-2 kernel K3 (one FPGA PE task: sw_pe_array_proc_element.v:1593-1685).
@@ -89,6 +113,13 @@ struct LaunchArgs {
     int32_t          nqw_max;      // max query words per lane over the launch (K1)
     int32_t          wmax;         // max band over the launch (K2: decides whether the row buffer may be a ring)
     int32_t          ring_cols;    // K2S: columns of the per-task row ring (power of two)
+    // lean output (flat batches planned on the device): the final 24-byte record {score,qle,tle,gtle,gscore,max_off} at
+    // out24[out_index[slot]] -- task order, ready for one D2H into the caller's array -- the cell count in cells_out (may
+    // be null) and every task with a non-zero status appended to flag_list as (status << 28 | task)
+    int32_t*  out24;
+    uint32_t* cells_out;
+    uint32_t* flag_list;           // [0] = number of entries, entries from [1]
+    uint32_t  flag_cap;
     // K3 (fused seed task) only: tiles come in (left, right) pairs, seeds[pair*32 + lane]
     const SeedParam* seeds;
     int32_t          w, pen_clip5, pen_clip3;

@@ -35,6 +35,8 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+constexpr uint32_t LEAN_FLAGS = 1023;      // flagged tasks a lean chunk reports in its first D2H (more: the list is fetched again)
+
 // One staging slot = one in-flight chunk on one stream.
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -55,11 +57,24 @@ struct Slot {
     unsigned char* d_rawt = nullptr; size_t d_rawt_cap = 0;
     uint32_t* d_flags = nullptr;     size_t d_flags_cap = 0;
     bool raw_mode = false;
+    // device-side scheduling (bsw_plan.cu): the input block then carries the tasks in input order (off_slots / off_ssrc
+    // / off_oidx = task params / task sources / task classes) and the slot arrays live in d_plan, written by the device
+    bool dp_mode = false;
+    unsigned char* d_plan = nullptr; size_t d_plan_cap = 0;
+    size_t dp_off_ssrc = 0, dp_off_oidx = 0;
+    // lean mode (flat batch, registered bases, device planner): 24-byte records in task order, straight into the
+    // caller's array when that is page-locked too; flags = [count | entries...] of tasks with a non-zero status
+    bool lean = false, lean_direct = false, lean_cells = false;
+    int32_t* d_out24 = nullptr; size_t d_out24_cap = 0;      // 6 x int32 per task
+    int32_t* h_out24 = nullptr; size_t h_out24_cap = 0;
+    uint32_t* d_cellsv = nullptr; size_t d_cellsv_cap = 0;
+    uint32_t* h_cellsv = nullptr; size_t h_cellsv_cap = 0;
+    uint32_t* d_flaglist = nullptr; uint32_t* h_flaglist = nullptr;      // LEAN_FLAGS + 1 words each
     const uint32_t*  d_src() const { return reinterpret_cast<const uint32_t*>(d_in); }
     const TileHdr*   d_tiles() const { return reinterpret_cast<const TileHdr*>(d_in + off_tiles); }
-    const SlotParam* d_slots() const { return reinterpret_cast<const SlotParam*>(d_in + off_slots); }
-    const SlotSrc*   d_ssrc() const { return reinterpret_cast<const SlotSrc*>(d_in + off_ssrc); }
-    const uint32_t*  d_oidx() const { return reinterpret_cast<const uint32_t*>(d_in + off_oidx); }
+    const SlotParam* d_slots() const { return dp_mode ? reinterpret_cast<const SlotParam*>(d_plan) : reinterpret_cast<const SlotParam*>(d_in + off_slots); }
+    const SlotSrc*   d_ssrc() const { return dp_mode ? reinterpret_cast<const SlotSrc*>(d_plan + dp_off_ssrc) : reinterpret_cast<const SlotSrc*>(d_in + off_ssrc); }
+    const uint32_t*  d_oidx() const { return dp_mode ? reinterpret_cast<const uint32_t*>(d_plan + dp_off_oidx) : reinterpret_cast<const uint32_t*>(d_in + off_oidx); }
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
     // in-flight bookkeeping
@@ -88,6 +103,11 @@ struct Device {
     Slot aux;                        // stream for measurement kernels
 };
 
+struct FlatSrc {
+    const bsw_params* p; const BandClamp* clamp; const uint8_t* qbuf; const int64_t* qoff; const uint8_t* tbuf; const int64_t* toff;
+    const int32_t* h0; const int32_t* w;
+};
+
 // Where a batch's tasks come from (flat arrays, bsw_task records, or an internal ExtTask vector).
 struct TaskSource {
     const void* self;
@@ -95,6 +115,8 @@ struct TaskSource {
     // raw mode: the bases of consecutive tasks are consecutive in two buffers the caller registered with bsw_host_register
     // (so the DMA engine can read them in place); a chunk's bases are then the byte ranges [task first .q, last .q + qlen)
     bool raw = false;
+    const FlatSrc* flat = nullptr;      // set for flat batches: the lean path reads the caller's arrays directly
+    bool out_registered = false;               // the caller's result array is page-locked: results are copied straight into it
 };
 
 }  // namespace
@@ -105,11 +127,12 @@ struct bsw_ctx {
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 16384;
-    int slots_per_worker = 2;
+    int slots_per_worker = 3;      // chunks one worker keeps in flight (3 measured 5-20 % faster than 2 once the host work is small)
     int raw_inputs = 2;            // flat batches whose base buffers are registered (bsw_host_register) skip the host packer:
                                    // 0 never, 1 always, 2 auto (when there are at most 10 host threads per GPU)
     std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
+    bool device_plan = true;       // the chunk's sort + tile building run on the device (bsw_plan.cu); false: host build_plan
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     cudaEvent_t trace_ref = nullptr;   // BSW_TRACE: recorded at the start of a batch call, origin of the per-chunk GPU timeline
     double trace_ref_host_ms = 0;      // host time (relative to the call start) at which trace_ref was recorded
@@ -208,6 +231,13 @@ void slot_free(Slot& s)
     if (s.d_rawq) cudaFree(s.d_rawq);
     if (s.d_rawt) cudaFree(s.d_rawt);
     if (s.d_flags) cudaFree(s.d_flags);
+    if (s.d_plan) cudaFree(s.d_plan);
+    if (s.d_out24) cudaFree(s.d_out24);
+    if (s.h_out24) cudaFreeHost(s.h_out24);
+    if (s.d_cellsv) cudaFree(s.d_cellsv);
+    if (s.h_cellsv) cudaFreeHost(s.h_cellsv);
+    if (s.d_flaglist) cudaFree(s.d_flaglist);
+    if (s.h_flaglist) cudaFreeHost(s.h_flaglist);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -273,6 +303,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         LaunchArgs a{};
         a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index; a.slot_flags = s.raw_mode ? s.d_flags : nullptr;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
+        if (s.lean) { a.out24 = s.d_out24; a.cells_out = s.lean_cells ? s.d_cellsv : nullptr; a.flag_list = s.d_flaglist; a.flag_cap = LEAN_FLAGS; }
         const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
@@ -300,6 +331,7 @@ int enqueue_gather(bsw_ctx* ctx, Slot& s)
     GatherArgs g{};
     g.tiles = s.d_tiles(); g.slots = s.d_slots(); g.slot_src = s.d_ssrc(); g.src = s.d_src(); g.dst = s.d_arena; g.ntiles = P.n_k1_tiles;
     if (s.raw_mode) { g.raw_q = s.d_rawq; g.raw_t = s.d_rawt; g.slot_flags = s.d_flags; }
+    if (s.dp_mode) g.dp_tiles = reinterpret_cast<TileHdr*>(s.d_in + s.off_tiles);
     cudaError_t e = k0_launch(g, s.stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "K0 gather launch");
     return 0;
@@ -326,7 +358,7 @@ bool raw_chunk_eligible(const ExtTask* t, size_t count, int max_mat, const Sched
 }
 
 int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, const DevParams& dp, int sym,
-                const SchedOptions& opt, bool timing, LocalStats* st, bool raw = false)
+                const SchedOptions& opt, bool timing, LocalStats* st, bool raw = false, bool allow_dp = false)
 {
     const double t0 = now_ms();
     int rc;
@@ -360,14 +392,36 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
         }
     }
     const double t1 = now_ms();
-    build_plan(s.tasks.data(), s.cls.data(), s.src.data(), count, opt, &s.plan);
+    DpGeometry geo{};
+    s.dp_mode = allow_dp && build_dp_plan(s.tasks.data(), s.cls.data(), count, opt, &s.plan, &geo);
+    if (!s.dp_mode) build_plan(s.tasks.data(), s.cls.data(), s.src.data(), count, opt, &s.plan);
     Plan& P = s.plan;
-    const size_t nslots = P.slots.size();
+    const size_t nslots = s.dp_mode ? geo.nslots : P.slots.size();
     s.off_tiles = (s.src_words * 4 + 15) & ~(size_t)15;
     s.off_slots = s.off_tiles + P.tiles.size() * sizeof(TileHdr);
-    s.off_ssrc = s.off_slots + nslots * sizeof(SlotParam);
-    s.off_oidx = s.off_ssrc + nslots * sizeof(SlotSrc);
-    s.in_bytes = s.off_oidx + nslots * sizeof(uint32_t);
+    DpArgs da{};
+    if (s.dp_mode) {
+        // input block: [source arena | TileHdr[] | task SlotParam[count] | task SlotSrc[count] | task class[count]]
+        s.off_ssrc = s.off_slots + count * sizeof(SlotParam);
+        s.off_oidx = s.off_ssrc + count * sizeof(SlotSrc);
+        s.in_bytes = (s.off_oidx + count + 15) & ~(size_t)15;
+        // device arrays the planner writes: slot scalars, slot sources, slot -> task index
+        s.dp_off_ssrc = nslots * sizeof(SlotParam);
+        s.dp_off_oidx = s.dp_off_ssrc + nslots * sizeof(SlotSrc);
+        const size_t off_bin = (s.dp_off_oidx + nslots * sizeof(uint32_t) + 15) & ~(size_t)15;
+        const size_t off_tbin = off_bin + (size_t)geo.nmajor * dp_bins_per_major() * sizeof(uint32_t);
+        if ((rc = grow_device(ctx, &s.d_plan, &s.d_plan_cap, off_tbin + count * sizeof(uint32_t)))) return rc;
+        da.count = (uint32_t)count; da.ntiles = geo.ntiles; da.nmajor = geo.nmajor;
+        memcpy(da.major_start, geo.major_start, sizeof(da.major_start)); memcpy(da.major_of, geo.major_of, sizeof(da.major_of));
+        da.bins = reinterpret_cast<uint32_t*>(s.d_plan + off_bin); da.task_bin = reinterpret_cast<uint32_t*>(s.d_plan + off_tbin);
+        for (int c = 0; c < 2; ++c) { da.class_count[c] = geo.class_count[c]; da.class_pos0[c] = geo.class_pos0[c]; da.class_slot0[c] = geo.class_slot0[c]; da.class_tile0[c] = geo.class_tile0[c]; }
+        da.slots = reinterpret_cast<SlotParam*>(s.d_plan); da.slot_src = reinterpret_cast<SlotSrc*>(s.d_plan + s.dp_off_ssrc);
+        da.out_index = reinterpret_cast<uint32_t*>(s.d_plan + s.dp_off_oidx);
+    } else {
+        s.off_ssrc = s.off_slots + nslots * sizeof(SlotParam);
+        s.off_oidx = s.off_ssrc + nslots * sizeof(SlotSrc);
+        s.in_bytes = s.off_oidx + nslots * sizeof(uint32_t);
+    }
     if (s.in_bytes > s.h_in_cap) { set_error(ctx, "internal: input block bound exceeded"); return BSW_ENOMEM; }
     if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, count))) return rc;
     if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
@@ -379,9 +433,19 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
         if ((rc = grow_device(ctx, &s.d_flags, &s.d_flags_cap, nslots))) return rc;
     }
     memcpy(s.h_in + s.off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
-    memcpy(s.h_in + s.off_slots, P.slots.data(), nslots * sizeof(SlotParam));
-    memcpy(s.h_in + s.off_ssrc, P.slot_src.data(), nslots * sizeof(SlotSrc));
-    {
+    if (s.dp_mode) {
+        SlotParam* tp = reinterpret_cast<SlotParam*>(s.h_in + s.off_slots);
+        const ExtTask* t = s.tasks.data();
+        for (size_t k = 0; k < count; ++k) tp[k] = SlotParam{ t[k].qlen, t[k].tlen, t[k].h0, t[k].w };
+        memcpy(s.h_in + s.off_ssrc, s.src.data(), count * sizeof(SlotSrc));
+        memcpy(s.h_in + s.off_oidx, s.cls.data(), count);
+        da.task_param = reinterpret_cast<const SlotParam*>(s.d_in + s.off_slots);
+        da.task_src = reinterpret_cast<const SlotSrc*>(s.d_in + s.off_ssrc);
+        da.task_cls = reinterpret_cast<const uint8_t*>(s.d_in + s.off_oidx);
+        da.tiles = reinterpret_cast<TileHdr*>(s.d_in + s.off_tiles);
+    } else {
+        memcpy(s.h_in + s.off_slots, P.slots.data(), nslots * sizeof(SlotParam));
+        memcpy(s.h_in + s.off_ssrc, P.slot_src.data(), nslots * sizeof(SlotSrc));
         uint32_t* oi = reinterpret_cast<uint32_t*>(s.h_in + s.off_oidx);
         for (size_t k = 0; k < nslots; ++k) oi[k] = (uint32_t)P.slot_task[k];      // padding lanes (-1) never write
     }
@@ -395,8 +459,13 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
         CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawt, s.tasks[0].t, raw_tbytes, cudaMemcpyHostToDevice, s.stream));
     }
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    if (s.dp_mode) {
+        const cudaError_t e = dp_plan_launch(da, s.stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "device planner launch");
+    }
     if ((rc = enqueue_gather(ctx, s))) return rc;
     if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub, s.d_oidx()))) return rc;
+    if (s.dp_mode) s.nlaunch += 3;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, count * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_out, s.stream));
@@ -413,11 +482,166 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
     return 0;
 }
 
+
+// ---- lean path: flat batch, bases in registered memory, scheduling on the device ----
+// One pass over the caller's offset / h0 / w arrays writes the chunk's tasks straight into the pinned input block
+// (24 bytes read, 24 written per task: no ExtTask records, no class bytes, no slot arrays) and keeps the per-bucket
+// counts the launch geometry needs; the bases are copied by the DMA engine where they lie; the kernels leave the final
+// 24-byte records in task order, so the results need one D2H -- into the caller's array itself when that is registered
+// too -- and the host never touches them.  Returns 1 when the chunk is not eligible (the caller then takes the
+// general path, which also words the error messages), 0 on success, < 0 on error.
+int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size_t count, int max_mat, const DevParams& dp, int sym,
+                     const SchedOptions& opt, bool timing, LocalStats* st, bsw_result* out, bool out_registered, bool want_cells)
+{
+    const double t0 = now_ms();
+    if (opt.force_kernel == 2 || opt.pair || opt.ring || count == 0) return 1;
+    int rc;
+    const size_t max_tiles = count / TILE_LANES + 8;
+    const size_t off_param = 0, off_src = count * sizeof(SlotParam);
+    const size_t off_tiles = (off_src + count * sizeof(SlotSrc) + 15) & ~(size_t)15;
+    const size_t in_bound = off_tiles + max_tiles * sizeof(TileHdr) + 64;
+    if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bound))) return rc;
+    SlotParam* tp = reinterpret_cast<SlotParam*>(s.h_in + off_param);
+    SlotSrc* ts = reinterpret_cast<SlotSrc*>(s.h_in + off_src);
+    const int64_t* qoff = F.qoff + first; const int64_t* toff = F.toff + first;
+    const int32_t* h0 = F.h0 + first; const int32_t* w = F.w + first;
+    const int64_t q0 = qoff[0], tt0 = toff[0];
+    const int qcap = opt.force_kernel == 0 ? std::min(K1_QLEN_CAP, opt.k2_min_qlen - 1) : K1_QLEN_CAP;
+    const int cl = opt.fast_matrix ? 0 : 1;
+    const BandClamp& clamp = *F.clamp;
+    DpBuckets bks;
+    memset(&bks, 0, sizeof(bks));
+    for (size_t k = 0; k < count; ++k) {
+        const int64_t ql = qoff[k + 1] - qoff[k], tl = toff[k + 1] - toff[k];
+        const int64_t qo = qoff[k] - q0, to = toff[k] - tt0;
+        if (ql < 1 || tl < 1 || ql > qcap || tl > 500000 || h0[k] < 1 || w[k] < 0 || qo < 0 || to < 0 ||
+            qo >= 0x7fff0000 || to >= 0x7fff0000 || (int64_t)h0[k] + ql * max_mat > SCORE_CAP) return 1;
+        const int wc = clamp((int)ql, w[k]);
+        tp[k] = SlotParam{ (int32_t)ql, (int32_t)tl, h0[k], wc };
+        ts[k] = SlotSrc{ (uint32_t)qo, (uint32_t)to };
+        bks.add(cl, (int)ql, (int)tl, wc);
+    }
+    const size_t raw_qbytes = (size_t)(qoff[count] - q0), raw_tbytes = (size_t)(toff[count] - tt0);
+    if (raw_qbytes >= 0x7fff0000u || raw_tbytes >= 0x7fff0000u) return 1;
+    const double t1 = now_ms();
+    DpGeometry geo{};
+    if (!dp_geometry(bks, count, opt, &s.plan, &geo)) return 1;
+    Plan& P = s.plan;
+    if (P.tiles.size() > max_tiles) { set_error(ctx, "internal: tile bound exceeded"); return BSW_ENOMEM; }
+    const size_t nslots = geo.nslots;
+    s.raw_mode = true; s.dp_mode = true; s.lean = true; s.lean_direct = out_registered; s.lean_cells = want_cells;
+    s.src_words = 0;
+    s.off_tiles = off_tiles; s.off_slots = off_param; s.off_ssrc = off_src; s.off_oidx = 0;
+    s.in_bytes = off_tiles + P.tiles.size() * sizeof(TileHdr);
+    memcpy(s.h_in + off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
+    s.dp_off_ssrc = nslots * sizeof(SlotParam);
+    s.dp_off_oidx = s.dp_off_ssrc + nslots * sizeof(SlotSrc);
+    const size_t off_bin = (s.dp_off_oidx + nslots * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t off_tbin = off_bin + (size_t)geo.nmajor * dp_bins_per_major() * sizeof(uint32_t);
+    if ((rc = grow_device(ctx, &s.d_plan, &s.d_plan_cap, off_tbin + count * sizeof(uint32_t)))) return rc;
+    if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
+    if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.tiled_words))) return rc;
+    if ((rc = grow_device(ctx, &s.d_rawq, &s.d_rawq_cap, raw_qbytes + 32))) return rc;
+    if ((rc = grow_device(ctx, &s.d_rawt, &s.d_rawt_cap, raw_tbytes + 32))) return rc;
+    if ((rc = grow_device(ctx, &s.d_flags, &s.d_flags_cap, nslots))) return rc;
+    if ((rc = grow_device(ctx, &s.d_out24, &s.d_out24_cap, count * 6))) return rc;
+    if (!out_registered && (rc = grow_pinned(ctx, &s.h_out24, &s.h_out24_cap, count * 6))) return rc;
+    if (want_cells) {
+        if ((rc = grow_device(ctx, &s.d_cellsv, &s.d_cellsv_cap, count))) return rc;
+        if ((rc = grow_pinned(ctx, &s.h_cellsv, &s.h_cellsv_cap, count))) return rc;
+    }
+    if (!s.d_flaglist) {
+        CUDA_TRY(ctx, cudaMalloc((void**)&s.d_flaglist, (LEAN_FLAGS + 1) * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaHostAlloc((void**)&s.h_flaglist, (LEAN_FLAGS + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    }
+    DpArgs da{};
+    da.count = (uint32_t)count; da.ntiles = geo.ntiles; da.nmajor = geo.nmajor;
+    memcpy(da.major_start, geo.major_start, sizeof(da.major_start)); memcpy(da.major_of, geo.major_of, sizeof(da.major_of));
+    for (int c = 0; c < 2; ++c) { da.class_count[c] = geo.class_count[c]; da.class_pos0[c] = geo.class_pos0[c]; da.class_slot0[c] = geo.class_slot0[c]; da.class_tile0[c] = geo.class_tile0[c]; }
+    da.bins = reinterpret_cast<uint32_t*>(s.d_plan + off_bin); da.task_bin = reinterpret_cast<uint32_t*>(s.d_plan + off_tbin);
+    da.slots = reinterpret_cast<SlotParam*>(s.d_plan); da.slot_src = reinterpret_cast<SlotSrc*>(s.d_plan + s.dp_off_ssrc);
+    da.out_index = reinterpret_cast<uint32_t*>(s.d_plan + s.dp_off_oidx);
+    da.task_param = reinterpret_cast<const SlotParam*>(s.d_in + off_param);
+    da.task_src = reinterpret_cast<const SlotSrc*>(s.d_in + off_src);
+    da.task_cls = nullptr; da.const_cls = (uint32_t)cl;
+    da.tiles = reinterpret_cast<TileHdr*>(s.d_in + off_tiles);
+    const double t2 = now_ms();
+
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_in, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawq, F.qbuf + q0, raw_qbytes, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawt, F.tbuf + tt0, raw_tbytes, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_flaglist, 0, sizeof(uint32_t), s.stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    {
+        const cudaError_t e = dp_plan_launch(da, s.stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "device planner launch");
+    }
+    if ((rc = enqueue_gather(ctx, s))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, true, &s.nlaunch, false, s.d_oidx()))) return rc;
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_registered ? (void*)(out + first) : (void*)s.h_out24, s.d_out24, count * sizeof(bsw_result),
+                                  cudaMemcpyDeviceToHost, s.stream));
+    if (want_cells) CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cellsv, s.d_cellsv, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_flaglist, s.d_flaglist, (LEAN_FLAGS + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.h_cells, s.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_out, s.stream));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_done, s.stream));
+    s.timed = timing;
+    s.busy = true; s.first = first; s.count = count;
+    s.nlaunch += 4;                                         // 3 planner kernels + the gather
+    st->validate_ms += t1 - t0;
+    st->pack_ms += t2 - t1;
+    s.trace_ms[0] = t1 - t0; s.trace_ms[1] = t2 - t1; s.trace_ms[2] = now_ms() - t2;
+    st->h2d += s.in_bytes + raw_qbytes + raw_tbytes;
+    st->d2h += count * sizeof(bsw_result) + (want_cells ? count * sizeof(uint32_t) : 0) + (LEAN_FLAGS + 1) * sizeof(uint32_t);
+    st->launches += s.nlaunch;
+    return 0;
+}
+
+int slot_collect_lean(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow,
+                      std::vector<size_t>* rerun_n)
+{
+    CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
+    s.busy = false; s.lean = false;
+    float ms = 0.f;
+    if (s.timed) CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    if (s.timed && ctx->trace_ref) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, ctx->trace_ref, s.ev_in); cudaEventElapsedTime(&b, ctx->trace_ref, s.ev_k0);
+        cudaEventElapsedTime(&c, ctx->trace_ref, s.ev_k1); cudaEventElapsedTime(&d, ctx->trace_ref, s.ev_out);
+        fprintf(stderr, "gpu chunk %zu+%zu: h2d %.3f..%.3f kernels ..%.3f d2h ..%.3f ms\n", s.first, s.count, a, b, c, d);
+    }
+    const size_t first = s.first, count = s.count;
+    if (!s.lean_direct) memcpy(out + first, s.h_out24, count * sizeof(bsw_result));
+    if (cells && s.lean_cells) memcpy(cells + first, s.h_cellsv, count * sizeof(uint32_t));
+    uint32_t nflag = s.h_flaglist[0];
+    std::vector<uint32_t> more;
+    const uint32_t* list = s.h_flaglist + 1;
+    if (nflag > LEAN_FLAGS) {
+        // more flagged tasks than the first copy holds (a batch full of N): the kernels stopped recording at the cap,
+        // so every task of the chunk is rerun on the staged path -- correct, just slower, and rare
+        for (size_t t = 0; t < count; ++t) rerun_n->push_back(first + t);
+        nflag = 0;
+    }
+    for (uint32_t k = 0; k < nflag; ++k) {
+        const uint32_t status = list[k] >> 28; const size_t t = first + (list[k] & 0x0fffffffu);
+        if (status == STATUS_OVERFLOW) overflow->push_back(t);
+        else if (status == STATUS_HAS_N) rerun_n->push_back(t);
+        else if (status == STATUS_BAD_CODE) { set_error(ctx, "task " + std::to_string(t) + ": invalid (base code > 4)"); return BSW_EINVAL; }
+        else { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
+    }
+    st->tasks += count; st->cells += *s.h_cells; st->kernel_ms += ms;
+    return 0;
+}
+
 // Wait for the slot's chunk and scatter its results to out[first + task].
 int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow,
                  std::vector<size_t>* rerun_n)
 {
     if (!s.busy) return 0;
+    if (s.lean) return slot_collect_lean(ctx, s, out, cells, st, overflow, rerun_n);
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
     s.busy = false;
     float ms = 0.f;
@@ -511,7 +735,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     // buffer, so it runs on chunks twice the usual size.
     const size_t ndev = ctx->devs.size();
     const bool allow_raw = src.raw && rerun_n_out != nullptr &&
-                           (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (size_t)opt.host_threads <= 10 * ndev));
+                           (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (ctx->device_plan || (size_t)opt.host_threads <= 10 * ndev)));
     size_t chunk = std::max<size_t>(32, allow_raw ? 2 * ctx->chunk_tasks : ctx->chunk_tasks);
     {
         const size_t probe = std::min<size_t>(n, 512);
@@ -526,8 +750,17 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
         const size_t per_worker = (n + (size_t)opt.host_threads - 1) / (size_t)opt.host_threads;
         chunk = std::min(chunk, std::max<size_t>(2048, (per_worker + 31) & ~(size_t)31));
     }
+    // The lean path leaves the host ~1 us per 1000 tasks of work, so what matters is the pipeline: every worker should own
+    // several chunks, or all the copies are issued at once and nothing overlaps (32 host threads, one 31 k task chunk
+    // each: 8.0 ms per 1 M tasks against 5.7 ms with 16 threads).  At most 8 workers per GPU, at least ~4 chunks each.
+    size_t max_workers = (size_t)opt.host_threads;
+    if (allow_raw && src.flat && ctx->device_plan) {
+        max_workers = std::min<size_t>(max_workers, 8 * ndev);
+        const size_t share = n / (max_workers * 4);
+        chunk = std::max<size_t>(std::min(chunk, std::max<size_t>(4096, (share + 31) & ~(size_t)31)), 32);
+    }
     const size_t nchunks = (n + chunk - 1) / chunk;
-    size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
+    size_t nworkers = std::min<size_t>(max_workers, nchunks);
     if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
     if (nworkers < 1) nworkers = 1;
     for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
@@ -573,13 +806,22 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
             const double c0 = T();
             if ((r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn))) break;
             if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(first) + "+" + std::to_string(count) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
+            if (allow_raw && src.flat && ctx->device_plan) {
+                r = slot_submit_lean(ctx, s, *src.flat, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, out, src.out_registered, cells != nullptr);
+                if (r <= 0) {
+                    if (trace) tr += " lean submitted " + std::to_string(T()) + " (pass " + std::to_string(s.trace_ms[0]) + " geometry " + std::to_string(s.trace_ms[1]) + " api " + std::to_string(s.trace_ms[2]) + ")\n";
+                    continue;
+                }
+                r = 0;                                   // not eligible: the general path below
+            }
             const double v0 = now_ms();
             s.tasks.resize(count);
             src.fill(src.self, first, count, s.tasks.data());
             st.validate_ms += now_ms() - v0;
             const double f1 = T();
             const bool raw = allow_raw && raw_chunk_eligible(s.tasks.data(), count, max_mat, opt);
-            r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, raw);
+            s.lean = false;
+            r = slot_submit(ctx, s, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, raw, ctx->device_plan);
             if (trace) tr += " fill.." + std::to_string(f1) + " submitted " + std::to_string(T()) + " (pack " + std::to_string(s.trace_ms[0]) +
                              " plan " + std::to_string(s.trace_ms[1]) + " api " + std::to_string(s.trace_ms[2]) + ")\n";
         }
@@ -656,10 +898,6 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
 }
 
 // ---- task sources ----
-struct FlatSrc {
-    const bsw_params* p; const BandClamp* clamp; const uint8_t* qbuf; const int64_t* qoff; const uint8_t* tbuf; const int64_t* toff;
-    const int32_t* h0; const int32_t* w;
-};
 void fill_flat(const void* self, size_t first, size_t count, ExtTask* out)
 {
     const FlatSrc& S = *static_cast<const FlatSrc*>(self);
@@ -792,6 +1030,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "k2_warps") { if (value != 1 && value != 4) return BSW_EINVAL; ctx->k2_warps = (int)value; }
     else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
+    else if (k == "device_plan") { ctx->device_plan = value != 0; }
     else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
@@ -825,6 +1064,8 @@ int bsw_extend_batch_flat(bsw_ctx* ctx, const bsw_params* params, const uint8_t*
     if (qoff[n] >= qoff[0] && toff[n] >= toff[0])
         src.raw = host_range_registered(ctx, qbuf + qoff[0], (size_t)(qoff[n] - qoff[0])) &&
                   host_range_registered(ctx, tbuf + toff[0], (size_t)(toff[n] - toff[0]));
+    src.flat = &S;
+    src.out_registered = host_range_registered(ctx, reinterpret_cast<const unsigned char*>(out), n * sizeof(bsw_result));
     return run_extensions(ctx, params, src, n, out, cells);
 }
 
@@ -1007,6 +1248,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     auto submit = [&](Slot& sl, size_t first, size_t range) -> int {
         int r = 0;
         sl.raw_mode = false;                     // the slot may have carried a raw-mode level-1 chunk before
+        sl.dp_mode = false;                      // ... or a device-planned one (the slot accessors follow the flag)
         sl.seed_idx.clear();
         {
             std::vector<size_t> left;

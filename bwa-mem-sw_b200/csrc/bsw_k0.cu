@@ -88,8 +88,16 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_c
     const uint32_t tile = blockIdx.x * K0_WARPS + (threadIdx.x >> 5);
     if (tile >= A.ntiles) return;
     const TileHdr hd = A.tiles[tile];
-    const int nqw = (int)(hd.nqw_ntw & 0x7fffu), ntw = (int)(hd.nqw_ntw >> 16);
+    int nqw = (int)(hd.nqw_ntw & 0x7fffu), ntw = (int)(hd.nqw_ntw >> 16);
     const SlotParam sp = A.slots[hd.slot0 + lane];
+    if (A.dp_tiles) {
+        // the device planner placed the tasks; the header's counts are the host's upper bounds (they size the arena):
+        // take the real ones so that K1 moves and walks no more words than the tile has
+        int tq = sp.qlen, tt = sp.tlen;
+        for (int o = 16; o; o >>= 1) { tq = max(tq, __shfl_xor_sync(0xffffffffu, tq, o)); tt = max(tt, __shfl_xor_sync(0xffffffffu, tt, o)); }
+        nqw = (tq + 7) >> 3; ntw = (tt + 7) >> 3;
+        if (lane == 0) A.dp_tiles[tile].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+    }
     const SlotSrc ss = A.slot_src[hd.slot0 + lane];
     const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0;      // words the host packed for this task (zero padded)
     const int own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;

@@ -68,9 +68,22 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
             if (f & SLOT_BAD_CODE) r.status = STATUS_BAD_CODE;
             else if (!GENERIC && (f & SLOT_HAS_N)) r.status = STATUS_HAS_N;      // the +a/-b cell cannot score an N
         }
-        int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
-        o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
-        o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
+        if (A.out24) {
+            const uint32_t task = A.out_index[slot];
+            int2* o = reinterpret_cast<int2*>(A.out24 + (size_t)task * 6);
+            o[0] = make_int2(r.score, r.qle);
+            o[1] = make_int2(r.tle, r.gtle);
+            o[2] = make_int2(r.gscore, r.max_off);
+            if (A.cells_out) A.cells_out[task] = (uint32_t)r.cells;
+            if (r.status != STATUS_OK) {
+                const uint32_t k = atomicAdd(A.flag_list, 1u);
+                if (k < A.flag_cap) A.flag_list[1 + k] = ((uint32_t)r.status << 28) | task;
+            }
+        } else {
+            int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
+            o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
+            o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
+        }
         my_cells = (uint32_t)r.cells;
     }
     if (A.cells_total) {                                 // one atomic per warp for the device-side cell counter

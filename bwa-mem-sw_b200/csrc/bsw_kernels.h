@@ -30,6 +30,10 @@ namespace bsw {
 // K0: tile gather (source arena -> tiled arena) for the K1 tiles of a chunk.
 cudaError_t k0_launch(const GatherArgs& a, cudaStream_t st);
 
+// Device-side scheduler: keys, radix sort, tile building for the K1 tasks of a chunk (bsw_plan.cu).
+cudaError_t dp_plan_launch(const DpArgs& a, cudaStream_t st);
+size_t dp_bins_per_major();     // u32 counters per non-empty (class, qlen/16) bucket in DpArgs.bins
+
 // K1: inter-task kernel (one lane per task, one warp-tile per CTA).  variant 1|2 (recurrence policy),
 // generic 0|1 (5x5 matrix lookup instead of match/mismatch), sym 0|1 (o_del==o_ins && e_del==e_ins).
 cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);

@@ -291,6 +291,83 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     plan->tiled_words = arena16 * 4 + 32;
 }
 
+bool build_dp_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g)
+{
+    if (n == 0 || opt.pair || opt.ring) return false;
+    DpBuckets bks;
+    memset(&bks, 0, sizeof(bks));
+    for (size_t i = 0; i < n; ++i) {
+        if (cls[i] & 6u) return false;                                   // a long task: the host planner handles the chunk
+        bks.add(cls[i] & 1, tasks[i].qlen, tasks[i].tlen, tasks[i].w);
+    }
+    return dp_geometry(bks, n, opt, plan, g);
+}
+
+bool dp_geometry(const DpBuckets& bks, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g)
+{
+    plan->tiles.clear(); plan->slots.clear(); plan->slot_src.clear(); plan->slot_task.clear(); plan->launches.clear();
+    plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
+    if (n == 0 || opt.pair || opt.ring) return false;
+    const DpBuckets::B (*bk)[128] = bks.bk;
+    static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
+    const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : (n >= 100000 ? 130 : 200));
+    size_t arena16 = 0;
+    uint32_t slot = 0, pos = 0;
+    g->nmajor = 0;
+    memset(g->major_of, 0, sizeof(g->major_of));
+    for (int c = 0; c < 2; ++c) {
+        uint32_t cnt = 0;
+        for (int b = 127; b >= 0; --b) {
+            if (!bk[c][b].cnt) continue;
+            if (g->nmajor >= 192) return false;
+            g->major_of[(c << 7) | b] = (uint8_t)g->nmajor;
+            g->major_start[g->nmajor++] = pos + cnt;
+            cnt += bk[c][b].cnt;
+        }
+        g->class_count[c] = cnt; g->class_pos0[c] = pos; g->class_slot0[c] = slot; g->class_tile0[c] = (uint32_t)plan->tiles.size();
+        pos += cnt;
+        if (!cnt) continue;
+        Launch L{};
+        L.kind = 1; L.generic = c; L.tile0 = (uint32_t)plan->tiles.size();
+        int occ0 = 0;
+        int b = 127;                                                     // buckets in sorted order: longest first
+        uint32_t left = bk[c][b].cnt;
+        for (uint32_t done = 0; done < cnt; done += TILE_LANES) {
+            int need = (int)std::min<uint32_t>(TILE_LANES, cnt - done);
+            int qmax = 0, tmax = 0, wmax = 0;
+            while (need > 0) {
+                while (left == 0) { --b; left = bk[c][b].cnt; }
+                const uint32_t take = std::min<uint32_t>(left, (uint32_t)need);
+                qmax = std::max(qmax, bk[c][b].maxq); tmax = std::max(tmax, bk[c][b].maxt); wmax = std::max(wmax, bk[c][b].maxw);
+                left -= take; need -= (int)take;
+            }
+            const int nqw = (qmax + 7) >> 3, ntw = (tmax + 7) >> 3;
+            TileHdr hd{};
+            hd.slot0 = slot; slot += TILE_LANES;
+            hd.qoff16 = (uint32_t)arena16; arena16 += (size_t)nqw * TILE_LANES * 4 / 16;
+            hd.toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
+            hd.nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
+            const int occ = occupancy(k1_tile_smem(qmax, nqw));
+            L.wmax = std::max(L.wmax, wmax);
+            if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw; }
+            else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw); }
+            else if (occ * 100 >= occ0 * bucket_pct) {
+                L.ntiles = (uint32_t)plan->tiles.size() - L.tile0;
+                if (L.ntiles) plan->launches.push_back(L);
+                L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw; L.wmax = wmax; occ0 = occ;
+            }
+            plan->tiles.push_back(hd);
+            ++plan->n_k1_tiles;
+        }
+        L.ntiles = (uint32_t)plan->tiles.size() - L.tile0;
+        if (L.ntiles) plan->launches.push_back(L);
+    }
+    g->ntiles = (uint32_t)plan->tiles.size();
+    g->nslots = slot;
+    plan->tiled_words = arena16 * 4 + 32;
+    return true;
+}
+
 static inline size_t k3_tile_smem(int qmax, int nqw)
 {
     return 128 + ((size_t)2 * (size_t)(nqw + 8) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;

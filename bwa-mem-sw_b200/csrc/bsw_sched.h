@@ -89,6 +89,30 @@ void build_seed_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* sr
 // Sort, tile, bucket.  Single-threaded: the driver runs one plan per chunk per host thread.
 void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, size_t n, const SchedOptions& opt, Plan* plan);
 
+// Device-side scheduling (bsw_plan.cu sorts and builds the slots): the host only needs the launch geometry, which
+// follows from per-bucket counts -- the sort key's major field is qlen/16, so class c's tiles are runs of buckets in
+// descending order.  Fills plan->tiles (offsets and slot0; word counts are upper bounds the device replaces),
+// plan->launches, n_k1_tiles, tiled_words.  Returns false when the chunk holds a task the device planner does not take
+// (long tasks: K2 / K1R classes), in which case build_plan must be used.
+struct DpGeometry {
+    uint32_t class_count[2], class_pos0[2], class_slot0[2], class_tile0[2]; uint32_t ntiles; size_t nslots;
+    uint32_t nmajor, major_start[192]; uint8_t major_of[256];      // non-empty (class, qlen/16) buckets in sorted order
+};
+bool build_dp_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g);
+// The two halves of build_dp_plan for callers that walk their tasks themselves (the lean flat path of bsw_host.cpp).
+struct DpBuckets {
+    struct B { uint32_t cnt; int maxq, maxt, maxw; } bk[2][128];         // [matrix class][qlen / 16]
+    void add(int cls, int qlen, int tlen, int w)
+    {
+        B& b = bk[cls & 1][qlen >> 4 < 127 ? qlen >> 4 : 127];
+        ++b.cnt;
+        if (qlen > b.maxq) b.maxq = qlen;
+        if (tlen > b.maxt) b.maxt = tlen;
+        if (w > b.maxw) b.maxw = w;
+    }
+};
+bool dp_geometry(const DpBuckets& bks, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g);
+
 // ksw_extend2's band clamp (public BWA algorithm; the RTL takes max_ins/max_del precomputed from the host:
 // sw_pe_array_proc_element.v:924-934 and applies them at sw_pe_array_sw_extend.v:1763-1765,1881,1890).
 int clamp_band(const int8_t mat[25], int qlen, int w, int end_bonus, int o_ins, int e_ins, int o_del, int e_del);

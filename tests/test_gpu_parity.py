@@ -271,14 +271,26 @@ def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
         P2 = B.make_params2(p, w=100, pen_clip5=5, pen_clip3=5)
         want2, _ = oracle_chain2aln(O, B, P2, seeds)
         assert_same(want2, ctx.proc_element_batch(P2, seeds), "level 2 after raw mode")
-        # auto: with a couple of host threads the raw path is taken, with many the staged one
+        # auto: with the device planner (default) the raw path is taken whatever the host has; with the host planner
+        # only when host threads are scarce
         ctx.set_option("raw_inputs", 2)
-        for threads, expect_raw in ((2, True), (16, False)):
-            ctx.set_option("host_threads", threads)
+        for plan, threads, expect_raw in ((1, 2, True), (1, 16, True), (0, 2, True), (0, 16, False)):
+            ctx.set_option("host_threads", threads); ctx.set_option("device_plan", plan)
             ctx.reset_stats()
-            r7, _ = ctx.sw_extend_batch(p, *flat)
-            assert_same(ro, r7, f"auto, {threads} host threads")
+            r7, c7 = ctx.sw_extend_batch(p, *flat)
+            assert_same(ro, r7, f"auto, {threads} host threads, device_plan {plan}")
+            assert_same(co.astype(np.int64), c7.astype(np.int64), "cells")
             assert (ctx.stats()["h2d_bytes"] > int(t["qoff"][-1] + t["toff"][-1])) == expect_raw
+        ctx.set_option("device_plan", 1)
+        # the caller's result array page-locked as well: the records are copied straight into it
+        out = np.zeros(len(ro), dtype=B.RESULT_DTYPE)
+        ctx.register_host(out)
+        try:
+            r8, c8 = ctx.sw_extend_batch(p, *flat, out=out)
+            assert r8 is out or np.shares_memory(r8, out)
+            assert_same(ro, out, "results DMA-ed into the registered array"); assert_same(co.astype(np.int64), c8.astype(np.int64), "cells")
+        finally:
+            ctx.unregister_host(out)
         ctx.set_option("host_threads", 0)
     finally:
         ctx.set_option("raw_inputs", 2); ctx.set_option("host_threads", 0)
