@@ -218,6 +218,9 @@ class Context:
             raise BswError(rc, "bsw_init failed (no usable sm_100 CUDA device? there is no CPU fallback)")
         for k, v in options.items():
             self.set_option(k, v)
+        for kv in filter(None, os.environ.get("BSW_OPTIONS", "").split(",")):      # experiments: BSW_OPTIONS="raw_inputs=3,slots=2"
+            k, _, v = kv.partition("=")
+            self.set_option(k.strip(), int(v))
 
     def close(self):
         if self.handle:

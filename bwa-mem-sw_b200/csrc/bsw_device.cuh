@@ -65,6 +65,7 @@ struct GatherArgs {
     const uint8_t*   raw_q;
     const uint8_t*   raw_t;
     uint32_t*        slot_flags;   // per slot: SLOT_HAS_N | SLOT_BAD_CODE
+    const uint32_t*  src2;         // lean path, 2 bit per base: SlotSrc then holds WORD offsets into src2 (16 bases per word)
     TileHdr*         dp_tiles;     // device-planned chunk: the gather takes the tiles' word counts (warp max) into the headers
 };
 

@@ -65,6 +65,7 @@ struct Slot {
     // lean mode (flat batch, registered bases, device planner): 24-byte records in task order, straight into the
     // caller's array when that is page-locked too; flags = [count | entries...] of tasks with a non-zero status
     bool lean = false, lean_direct = false, lean_cells = false;
+    size_t off_arena2 = 0;         // lean path with host-packed 2-bit bases: offset of the packed arena in the input block (0: raw bases)
     int32_t* d_out24 = nullptr; size_t d_out24_cap = 0;      // 6 x int32 per task
     int32_t* h_out24 = nullptr; size_t h_out24_cap = 0;
     uint32_t* d_cellsv = nullptr; size_t d_cellsv_cap = 0;
@@ -282,7 +283,7 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
 }
 
 // Host statistics accumulated by one worker and merged once per call.
-struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0; };
+struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0, packed_chunks = 0, raw_chunks = 0; };
 
 int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, bool k2_sub, const uint32_t* out_index)
 {
@@ -331,6 +332,7 @@ int enqueue_gather(bsw_ctx* ctx, Slot& s)
     GatherArgs g{};
     g.tiles = s.d_tiles(); g.slots = s.d_slots(); g.slot_src = s.d_ssrc(); g.src = s.d_src(); g.dst = s.d_arena; g.ntiles = P.n_k1_tiles;
     if (s.raw_mode) { g.raw_q = s.d_rawq; g.raw_t = s.d_rawt; g.slot_flags = s.d_flags; }
+    if (s.lean && s.off_arena2) g.src2 = reinterpret_cast<const uint32_t*>(s.d_in + s.off_arena2);
     if (s.dp_mode) g.dp_tiles = reinterpret_cast<TileHdr*>(s.d_in + s.off_tiles);
     cudaError_t e = k0_launch(g, s.stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "K0 gather launch");
@@ -491,7 +493,8 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
 // too -- and the host never touches them.  Returns 1 when the chunk is not eligible (the caller then takes the
 // general path, which also words the error messages), 0 on success, < 0 on error.
 int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size_t count, int max_mat, const DevParams& dp, int sym,
-                     const SchedOptions& opt, bool timing, LocalStats* st, bsw_result* out, bool out_registered, bool want_cells)
+                     const SchedOptions& opt, bool timing, LocalStats* st, bsw_result* out, bool out_registered, bool want_cells,
+                     bool packed2, std::vector<size_t>* rerun_n)
 {
     const double t0 = now_ms();
     if (opt.force_kernel == 2 || opt.pair || opt.ring || count == 0) return 1;
@@ -499,7 +502,13 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
     const size_t max_tiles = count / TILE_LANES + 8;
     const size_t off_param = 0, off_src = count * sizeof(SlotParam);
     const size_t off_tiles = (off_src + count * sizeof(SlotSrc) + 15) & ~(size_t)15;
-    const size_t in_bound = off_tiles + max_tiles * sizeof(TileHdr) + 64;
+    const size_t off_arena2 = off_tiles + max_tiles * sizeof(TileHdr);
+    size_t in_bound = off_arena2 + 64;
+    if (packed2) {
+        const int64_t qb = F.qoff[first + count] - F.qoff[first], tb = F.toff[first + count] - F.toff[first];
+        if (qb < 0 || tb < 0 || qb >= 0x7fff0000 || tb >= 0x7fff0000) return 1;
+        in_bound += (size_t)(qb + tb) / 4 + 8 * count + 128;            // 2 bit per base, every sequence rounded up to a word
+    }
     if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bound))) return rc;
     SlotParam* tp = reinterpret_cast<SlotParam*>(s.h_in + off_param);
     SlotSrc* ts = reinterpret_cast<SlotSrc*>(s.h_in + off_src);
@@ -521,18 +530,28 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
         ts[k] = SlotSrc{ (uint32_t)qo, (uint32_t)to };
         bks.add(cl, (int)ql, (int)tl, wc);
     }
-    const size_t raw_qbytes = (size_t)(qoff[count] - q0), raw_tbytes = (size_t)(toff[count] - tt0);
+    size_t raw_qbytes = (size_t)(qoff[count] - q0), raw_tbytes = (size_t)(toff[count] - tt0);
     if (raw_qbytes >= 0x7fff0000u || raw_tbytes >= 0x7fff0000u) return 1;
+    size_t arena2_bytes = 0;
+    if (packed2) {
+        std::vector<uint32_t> n_tasks;
+        const int64_t words = pack2_flat(F.qbuf, qoff, F.tbuf, toff, count, reinterpret_cast<uint32_t*>(s.h_in + off_arena2), ts, &n_tasks);
+        if (words < 0) { set_error(ctx, "task " + std::to_string(first + (size_t)(-1 - words)) + ": invalid (base code > 4)"); return BSW_EINVAL; }
+        for (uint32_t k : n_tasks) rerun_n->push_back(first + k);            // an N has no 2-bit code: those tasks are rerun (4 bit, matrix lookup)
+        arena2_bytes = (size_t)words * 4 + 16;
+        raw_qbytes = raw_tbytes = 0;
+    }
     const double t1 = now_ms();
     DpGeometry geo{};
     if (!dp_geometry(bks, count, opt, &s.plan, &geo)) return 1;
     Plan& P = s.plan;
     if (P.tiles.size() > max_tiles) { set_error(ctx, "internal: tile bound exceeded"); return BSW_ENOMEM; }
     const size_t nslots = geo.nslots;
-    s.raw_mode = true; s.dp_mode = true; s.lean = true; s.lean_direct = out_registered; s.lean_cells = want_cells;
+    s.raw_mode = !packed2; s.dp_mode = true; s.lean = true; s.lean_direct = out_registered; s.lean_cells = want_cells;
+    s.off_arena2 = packed2 ? off_arena2 : 0;
     s.src_words = 0;
     s.off_tiles = off_tiles; s.off_slots = off_param; s.off_ssrc = off_src; s.off_oidx = 0;
-    s.in_bytes = off_tiles + P.tiles.size() * sizeof(TileHdr);
+    s.in_bytes = packed2 ? off_arena2 + arena2_bytes : off_tiles + P.tiles.size() * sizeof(TileHdr);
     memcpy(s.h_in + off_tiles, P.tiles.data(), P.tiles.size() * sizeof(TileHdr));
     s.dp_off_ssrc = nslots * sizeof(SlotParam);
     s.dp_off_oidx = s.dp_off_ssrc + nslots * sizeof(SlotSrc);
@@ -541,9 +560,11 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
     if ((rc = grow_device(ctx, &s.d_plan, &s.d_plan_cap, off_tbin + count * sizeof(uint32_t)))) return rc;
     if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bound))) return rc;
     if ((rc = grow_device(ctx, &s.d_arena, &s.d_arena_cap, P.tiled_words))) return rc;
-    if ((rc = grow_device(ctx, &s.d_rawq, &s.d_rawq_cap, raw_qbytes + 32))) return rc;
-    if ((rc = grow_device(ctx, &s.d_rawt, &s.d_rawt_cap, raw_tbytes + 32))) return rc;
-    if ((rc = grow_device(ctx, &s.d_flags, &s.d_flags_cap, nslots))) return rc;
+    if (!packed2) {
+        if ((rc = grow_device(ctx, &s.d_rawq, &s.d_rawq_cap, raw_qbytes + 32))) return rc;
+        if ((rc = grow_device(ctx, &s.d_rawt, &s.d_rawt_cap, raw_tbytes + 32))) return rc;
+        if ((rc = grow_device(ctx, &s.d_flags, &s.d_flags_cap, nslots))) return rc;
+    }
     if ((rc = grow_device(ctx, &s.d_out24, &s.d_out24_cap, count * 6))) return rc;
     if (!out_registered && (rc = grow_pinned(ctx, &s.h_out24, &s.h_out24_cap, count * 6))) return rc;
     if (want_cells) {
@@ -569,8 +590,10 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
 
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_in, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in, s.h_in, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawq, F.qbuf + q0, raw_qbytes, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawt, F.tbuf + tt0, raw_tbytes, cudaMemcpyHostToDevice, s.stream));
+    if (!packed2) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawq, F.qbuf + q0, raw_qbytes, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.d_rawt, F.tbuf + tt0, raw_tbytes, cudaMemcpyHostToDevice, s.stream));
+    }
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_flaglist, 0, sizeof(uint32_t), s.stream));
     CUDA_TRY(ctx, cudaMemsetAsync(s.d_cells, 0, sizeof(unsigned long long), s.stream));
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
@@ -734,8 +757,22 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     // (16 threads: 6.5 vs 5.8 ms), so "auto" takes it only when the host is the scarce side.  Its copies are per
     // buffer, so it runs on chunks twice the usual size.
     const size_t ndev = ctx->devs.size();
-    const bool allow_raw = src.raw && rerun_n_out != nullptr &&
-                           (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (ctx->device_plan || (size_t)opt.host_threads <= 10 * ndev)));
+    // Flat batches planned on the device take the lean path: 2 = the host packs the bases 2 bit each (any memory), 1 = the
+    // DMA engine copies them one byte each from registered buffers (no host pass over the bases at all).  Packing costs
+    // ~8 ns per task and thread and cuts the host->device bytes 2.5x, so "auto" packs unless a GPU has a single host thread.
+    // "auto": raw whenever the buffers are registered, packed otherwise.  Measured on an 8-GPU box (32 host cores, 4 per
+    // GPU): raw 11.3 ms per step (GPUs 0-3 sit behind a slower root complex: 20 GB/s each when all eight copy), packed
+    // 17.6 ms (the cores read 8 x 190 MB per step: the host memory system is the limit), a per-chunk switch on "are the
+    // previous chunk's copies still in flight" 20.1 ms (it packs about half of the chunks).  With 16 cores for one GPU
+    // packed is the faster one by 3-10 % (5.5 vs 5.7-6.0 ms) -- not worth a rule that can misfire.
+    int lean_mode = 0;
+    if (src.flat && ctx->device_plan && rerun_n_out != nullptr) {
+        if (ctx->raw_inputs == 3) lean_mode = 2;
+        else if (ctx->raw_inputs == 1) lean_mode = src.raw ? 1 : 0;
+        else if (ctx->raw_inputs == 2) lean_mode = src.raw ? 1 : 2;
+    }
+    const bool allow_raw = lean_mode == 1 || (lean_mode == 0 && src.raw && rerun_n_out != nullptr &&
+                           (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (size_t)opt.host_threads <= 10 * ndev)));
     size_t chunk = std::max<size_t>(32, allow_raw ? 2 * ctx->chunk_tasks : ctx->chunk_tasks);
     {
         const size_t probe = std::min<size_t>(n, 512);
@@ -754,8 +791,8 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     // several chunks, or all the copies are issued at once and nothing overlaps (32 host threads, one 31 k task chunk
     // each: 8.0 ms per 1 M tasks against 5.7 ms with 16 threads).  At most 8 workers per GPU, at least ~4 chunks each.
     size_t max_workers = (size_t)opt.host_threads;
-    if (allow_raw && src.flat && ctx->device_plan) {
-        max_workers = std::min<size_t>(max_workers, 8 * ndev);
+    if (lean_mode) {
+        max_workers = std::min<size_t>(max_workers, (lean_mode >= 2 ? 16 : 8) * ndev);
         const size_t share = n / (max_workers * 4);
         chunk = std::max<size_t>(std::min(chunk, std::max<size_t>(4096, (share + 31) & ~(size_t)31)), 32);
     }
@@ -806,8 +843,11 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
             const double c0 = T();
             if ((r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn))) break;
             if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(first) + "+" + std::to_string(count) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
-            if (allow_raw && src.flat && ctx->device_plan) {
-                r = slot_submit_lean(ctx, s, *src.flat, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, out, src.out_registered, cells != nullptr);
+            if (lean_mode) {
+                const bool packed2 = lean_mode == 2;
+                r = slot_submit_lean(ctx, s, *src.flat, first, count, max_mat, dp, sym, opt, ctx->kernel_timing, &st, out, src.out_registered, cells != nullptr,
+                                     packed2, &rrn);
+                if (r == 0) { if (packed2) ++st.packed_chunks; else ++st.raw_chunks; }
                 if (r <= 0) {
                     if (trace) tr += " lean submitted " + std::to_string(T()) + " (pass " + std::to_string(s.trace_ms[0]) + " geometry " + std::to_string(s.trace_ms[1]) + " api " + std::to_string(s.trace_ms[2]) + ")\n";
                     continue;
@@ -1022,7 +1062,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     const std::string k(key);
     if (k == "variant") { if (value != 1 && value != 2) return BSW_EINVAL; ctx->opt.variant = (int)value; }
     else if (k == "host_threads") { if (value < 0 || value > 1024) return BSW_EINVAL; ctx->opt.host_threads = (int)value; }
-    else if (k == "raw_inputs") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->raw_inputs = (int)value; }
+    else if (k == "raw_inputs") { if (value < 0 || value > 3) return BSW_EINVAL; ctx->raw_inputs = (int)value; }
     else if (k == "slots") { if (value < 1 || value > 16) return BSW_EINVAL; ctx->slots_per_worker = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }

@@ -82,6 +82,24 @@ __device__ __forceinline__ uint32_t k0_pack_raw(const uint8_t* __restrict__ base
     return flags;
 }
 
+// 2 bit per base source (bsw_pack2.cpp): 16 bases per word, sequences start on a word.  Every source word becomes two
+// tile words (8 bases each, 4 bit per base): the 2-bit fields are spread to nibbles with three shift-and-mask steps.
+__device__ __forceinline__ uint32_t k0_spread16(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return x;
+}
+__device__ __forceinline__ void k0_unpack2(const uint32_t* __restrict__ src, int len, uint32_t* __restrict__ dst, int tile_words, int lane)
+{
+    for (int m = 0; 2 * m < tile_words; ++m) {
+        const uint32_t w = (16 * m < len) ? __ldg(src + m) : 0u;
+        dst[(size_t)(2 * m) * TILE_LANES + lane] = k0_spread16(w & 0xffffu);
+        if (2 * m + 1 < tile_words) dst[(size_t)(2 * m + 1) * TILE_LANES + lane] = k0_spread16(w >> 16);
+    }
+}
+
 __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_constant__ GatherArgs A)
 {
     const int lane = threadIdx.x & 31;
@@ -101,6 +119,11 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_c
     const SlotSrc ss = A.slot_src[hd.slot0 + lane];
     const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0;      // words the host packed for this task (zero padded)
     const int own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
+    if (A.src2) {
+        k0_unpack2(A.src2 + ss.qoff16, sp.qlen, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
+        k0_unpack2(A.src2 + ss.toff16, sp.tlen, A.dst + (size_t)hd.toff16 * 4, ntw, lane);
+        return;
+    }
     if (A.raw_q) {
         uint32_t f = k0_pack_raw(A.raw_q + ss.qoff16, sp.qlen, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
         f |= k0_pack_raw(A.raw_t + ss.toff16, sp.tlen, A.dst + (size_t)hd.toff16 * 4, ntw, lane);

@@ -79,6 +79,15 @@ int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& 
                 : pack_tasks_sse2(tasks, n, max_mat, opt, cls, src, arena, words_used, bad_task, msg);
 }
 
+int64_t pack2_flat(const uint8_t* qbuf, const int64_t* qoff, const uint8_t* tbuf, const int64_t* toff, size_t count,
+                   uint32_t* arena, SlotSrc* src, std::vector<uint32_t>* n_list)
+{
+    static const bool wide = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                             __builtin_cpu_supports("bmi2") && !getenv("BSW_NO_AVX512");
+    return wide ? pack2_flat_avx512(qbuf, qoff, tbuf, toff, count, arena, src, n_list)
+                : pack2_flat_generic(qbuf, qoff, tbuf, toff, count, arena, src, n_list);
+}
+
 // order[] = task indices by ascending 32-bit key (stable LSD radix).  The digit width follows the chunk size: three
 // 11-bit passes for the usual 8-32 k task chunk (the three histograms come from one pass over the keys and stay in
 // L1), two 16-bit passes for big plans (resident batches) where the per-pass traffic dominates.

@@ -80,6 +80,14 @@ int pack_tasks_sse2(const ExtTask* tasks, size_t n, int max_mat, const SchedOpti
 int pack_tasks_avx512(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                       uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
 
+// 2 bit per base packer of the lean flat path (bsw_pack2.cpp, two builds; pack2_flat dispatches on the CPU).
+int64_t pack2_flat_generic(const uint8_t* qbuf, const int64_t* qoff, const uint8_t* tbuf, const int64_t* toff, size_t count,
+                           uint32_t* arena, SlotSrc* src, std::vector<uint32_t>* n_list);
+int64_t pack2_flat_avx512(const uint8_t* qbuf, const int64_t* qoff, const uint8_t* tbuf, const int64_t* toff, size_t count,
+                          uint32_t* arena, SlotSrc* src, std::vector<uint32_t>* n_list);
+int64_t pack2_flat(const uint8_t* qbuf, const int64_t* qoff, const uint8_t* tbuf, const int64_t* toff, size_t count,
+                   uint32_t* arena, SlotSrc* src, std::vector<uint32_t>* n_list);
+
 // Level-2 plan: tasks[2*s] / tasks[2*s+1] are the left / right flank of seed s (qlen == 0: absent, cls 0x80).  The band
 // of a seed task is decided on the device, so ExtTask.w is free: a present right flank carries its score-budget hint
 // there (about h0 + left qlen), which only feeds the sort key.  Seeds are

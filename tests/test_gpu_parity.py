@@ -271,17 +271,31 @@ def test_registered_buffers_skip_the_staging_pass(B, O, ctx):
         P2 = B.make_params2(p, w=100, pen_clip5=5, pen_clip3=5)
         want2, _ = oracle_chain2aln(O, B, P2, seeds)
         assert_same(want2, ctx.proc_element_batch(P2, seeds), "level 2 after raw mode")
-        # auto: with the device planner (default) the raw path is taken whatever the host has; with the host planner
-        # only when host threads are scarce
+        # auto: with the device planner (default) every chunk goes raw or 2-bit packed depending on whether the copy engine
+        # keeps up (timing dependent: results only); with the host planner raw only when host threads are scarce
         ctx.set_option("raw_inputs", 2)
-        for plan, threads, expect_raw in ((1, 2, True), (1, 16, True), (0, 2, True), (0, 16, False)):
+        for plan, threads, expect_raw in ((1, 1, None), (1, 16, None), (0, 2, True), (0, 16, False)):
             ctx.set_option("host_threads", threads); ctx.set_option("device_plan", plan)
             ctx.reset_stats()
             r7, c7 = ctx.sw_extend_batch(p, *flat)
             assert_same(ro, r7, f"auto, {threads} host threads, device_plan {plan}")
             assert_same(co.astype(np.int64), c7.astype(np.int64), "cells")
-            assert (ctx.stats()["h2d_bytes"] > int(t["qoff"][-1] + t["toff"][-1])) == expect_raw
+            if expect_raw is not None:
+                assert (ctx.stats()["h2d_bytes"] > int(t["qoff"][-1] + t["toff"][-1])) == expect_raw
         ctx.set_option("device_plan", 1)
+        # 2 bit per base forced: N tasks are rerun, a bad code is reported with its task
+        ctx.set_option("raw_inputs", 3)
+        ctx.reset_stats()
+        r9, c9 = ctx.sw_extend_batch(p, *flat)
+        assert_same(ro, r9, "2-bit lean path"); assert_same(co.astype(np.int64), c9.astype(np.int64), "2-bit lean path cells")
+        assert ctx.stats()["h2d_bytes"] < (int(t["qoff"][-1] + t["toff"][-1])) // 2 + 40 * len(ro)
+        keep = t["qbuf"][int(t["qoff"][777]) + 1]
+        t["qbuf"][int(t["qoff"][777]) + 1] = 7
+        with pytest.raises(B.BswError) as e2:
+            ctx.sw_extend_batch(p, *flat)
+        t["qbuf"][int(t["qoff"][777]) + 1] = keep
+        assert e2.value.code == B.BSW_EINVAL and "task 777" in str(e2.value)
+        ctx.set_option("raw_inputs", 2)
         # the caller's result array page-locked as well: the records are copied straight into it
         out = np.zeros(len(ro), dtype=B.RESULT_DTYPE)
         ctx.register_host(out)
