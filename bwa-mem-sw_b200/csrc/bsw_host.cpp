@@ -133,6 +133,7 @@ struct bsw_ctx {
                                    // 0 never, 1 always, 2 auto (when there are at most 10 host threads per GPU)
     std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
+    bool k2_narrow = true;         // K2 rows below 64 columns run in registers (bsw_k2.cu::k2_narrow_row)
     bool device_plan = true;       // the chunk's sort + tile building run on the device (bsw_plan.cu); false: host build_plan
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
     cudaEvent_t trace_ref = nullptr;   // BSW_TRACE: recorded at the start of a batch call, origin of the per-chunk GPU timeline
@@ -304,6 +305,7 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         LaunchArgs a{};
         a.tiles = s.d_tiles() + L.tile0; a.slots = s.d_slots(); a.arena = (L.kind == 2) ? s.d_src() : s.d_arena; a.out = s.d_out; a.out_index = out_index; a.slot_flags = s.raw_mode ? s.d_flags : nullptr;
         a.cells_total = count_cells ? s.d_cells : nullptr; a.p = dp; a.ntiles = L.ntiles; a.qmax = L.qmax; a.nqw_max = L.nqw_max; a.wmax = L.wmax;
+        a.k2_narrow = ctx->k2_narrow ? 1 : 0;
         if (s.lean) { a.out24 = s.d_out24; a.cells_out = s.lean_cells ? s.d_cellsv : nullptr; a.flag_list = s.d_flaglist; a.flag_cap = LEAN_FLAGS; }
         const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
@@ -760,16 +762,16 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     // Flat batches planned on the device take the lean path: 2 = the host packs the bases 2 bit each (any memory), 1 = the
     // DMA engine copies them one byte each from registered buffers (no host pass over the bases at all).  Packing costs
     // ~8 ns per task and thread and cuts the host->device bytes 2.5x, so "auto" packs unless a GPU has a single host thread.
-    // "auto": raw whenever the buffers are registered, packed otherwise.  Measured on an 8-GPU box (32 host cores, 4 per
+    // "auto": raw when the buffers are registered and the GPU has fewer than 12 host threads to itself, packed otherwise.  Measured on an 8-GPU box (32 host cores, 4 per
     // GPU): raw 11.3 ms per step (GPUs 0-3 sit behind a slower root complex: 20 GB/s each when all eight copy), packed
     // 17.6 ms (the cores read 8 x 190 MB per step: the host memory system is the limit), a per-chunk switch on "are the
     // previous chunk's copies still in flight" 20.1 ms (it packs about half of the chunks).  With 16 cores for one GPU
-    // packed is the faster one by 3-10 % (5.5 vs 5.7-6.0 ms) -- not worth a rule that can misfire.
+    // packed is the faster one by 3-10 % (5.5 vs 5.7-6.0 ms per 1 M tasks).
     int lean_mode = 0;
     if (src.flat && ctx->device_plan && rerun_n_out != nullptr) {
         if (ctx->raw_inputs == 3) lean_mode = 2;
         else if (ctx->raw_inputs == 1) lean_mode = src.raw ? 1 : 0;
-        else if (ctx->raw_inputs == 2) lean_mode = src.raw ? 1 : 2;
+        else if (ctx->raw_inputs == 2) lean_mode = (src.raw && (size_t)opt.host_threads < 12 * ndev) ? 1 : 2;
     }
     const bool allow_raw = lean_mode == 1 || (lean_mode == 0 && src.raw && rerun_n_out != nullptr &&
                            (ctx->raw_inputs == 1 || (ctx->raw_inputs == 2 && (size_t)opt.host_threads <= 10 * ndev)));
@@ -1071,6 +1073,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "device_plan") { ctx->device_plan = value != 0; }
+    else if (k == "k2_narrow") { ctx->k2_narrow = value != 0; }
     else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }

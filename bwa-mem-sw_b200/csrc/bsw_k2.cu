@@ -51,6 +51,103 @@ __device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
     return (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
 }
 
+
+// ---- narrow rows (one warp per task) ----
+// With PacBio-like errors the narrowed window of a long task is ~50 columns wide (a few hundred at most), so the
+// 256-column group of the general path leaves most lanes idle: 5.1 G warp-instructions for 1.3 G cells in round 1, of
+// which ~7 lanes per instruction held live cells.  A row whose window is below 32*CPL columns runs here instead: ONE
+// round, lane l owns the CPL columns j0 + CPL*l + k (no alignment: the ring is addressed per word), everything stays in
+// registers.  The F recurrence is the same zero-carry prefix max, with a stride of CPL columns per lane; the band
+// narrowing needs no bit array: one ballot per k gives the zero cells as warp-uniform masks, and the two scans of the
+// reference (sx:1766-1769 / 1779,1782-1789) become two find-first/last-set on those masks.
+// Outputs: key = (row max << 16 | right-most column holding it), hlast = h of column lim-1, cb / ce = last zero cell
+// left of mj / first zero cell right of it (-1 / 0x7fffffff when there is none).
+template <int GENERIC, int CPL>
+__device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const uint32_t* __restrict__ qs, const int rm, const int nqw,
+                                              const int j0, const int lim, const int fc, const int lane, const uint32_t trep,
+                                              const uint32_t rlo, const uint32_t rhi, const int mat, const int mis,
+                                              const int e_ins, const int oe_ins, const int oe_del, const uint32_t ce_pack,
+                                              int& key_out, int& hlast, int& cb_out, int& ce_out)
+{
+    const int c0 = j0 + CPL * lane;
+    uint32_t wd[CPL];
+    int hh[CPL], fl[CPL], h[CPL];
+    bool live[CPL];
+    int run = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int c = c0 + k;
+        live[k] = c < lim;
+        wd[k] = live[k] ? eh[c & rm] : 0u;
+        const uint32_t qw = (live[k] && (c >> 3) < nqw) ? qs[c >> 3] : 0u;
+        const uint32_t nib = (qw >> (4 * (c & 7))) & 15u;
+        const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
+        const int sc = k2_score<GENERIC>(GENERIC ? nib : (nib ^ (trep & 15u)), mat, mis, rlo, rhi);
+        hh[k] = add_max(M, sc, e);                                                 // sx:1797,1798
+        int g = add_max_relu(hh[k], -oe_ins, 0);                                   // sx:1863,1865 with h >= hh
+        if (!live[k]) g = 0;
+        fl[k] = run;
+        run = add_max(run, -e_ins, g);                                             // sx:1780,1781
+    }
+    const int estep = CPL * e_ins;
+    int P = run + estep * lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, P, d);
+        if (lane >= d) P = imax(P, o);
+    }
+    const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
+    int u = (lane > 0) ? imax(Pex - estep * (lane - 1), 0) : 0;                    // f entering this lane's first column
+    int key = -1;
+    uint32_t enew[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int f = imax(fl[k], u);
+        u -= e_ins;
+        h[k] = imax(hh[k], f);                                                     // sx:1809
+        const int t = add_max_relu(h[k], -oe_del, 0);                              // sx:1866,1862
+        enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);                // {max(e-e_del,t), 0}  sx:1770-1771
+        if (live[k]) key = imax(key, h[k] * 65536 + c0 + k);                       // sx:1808,1816
+    }
+    int hleft = __shfl_up_sync(0xffffffffu, h[CPL - 1], 1);
+    if (lane == 0) hleft = fc;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int c = c0 + k;
+        if (c <= lim) {                                                            // cells and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
+            const int h1 = (c == j0) ? fc : (k ? h[k - 1] : hleft);
+            eh[c & rm] = (c < lim ? enew[k] : 0u) | (uint32_t)h1;
+        }
+    }
+    key = __reduce_max_sync(0xffffffffu, key);
+    const int mj = key & 0xffff;
+    // h of the last cell (column lim-1), for the gscore rule
+    {
+        const int d = lim - 1 - j0;
+        int v = h[0];
+        if (CPL == 2) v = (d & 1) ? h[1] : h[0];
+        hlast = __shfl_sync(0xffffffffu, v, d / CPL);
+    }
+    int cb = -1, ce = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const uint32_t z = __ballot_sync(0xffffffffu, live[k] && h[k] == 0);       // bit l <-> column j0 + CPL*l + k
+        const int la = mj - 1 - j0 - k;                                            // lanes l with column <= mj-1: CPL*l <= la
+        if (la >= 0) {
+            const int lmax = la / CPL;
+            const uint32_t m = z & (lmax >= 31 ? 0xffffffffu : ((2u << lmax) - 1u));
+            if (m) cb = imax(cb, j0 + CPL * (31 - __clz(m)) + k);
+        }
+        const int lb = mj + 1 - j0 - k;                                            // lanes l with column >= mj+1: CPL*l >= lb
+        const int lmin = lb <= 0 ? 0 : (lb + CPL - 1) / CPL;
+        if (lmin < 32) {
+            const uint32_t m = z & (0xffffffffu << lmin);
+            if (m) ce = imin(ce, j0 + CPL * (__ffs(m) - 1) + k);
+        }
+    }
+    key_out = key; cb_out = cb; ce_out = ce;
+}
+
 template <int NW> __device__ __forceinline__ void k2_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 
 template <int GENERIC, int K2_WARPS>
@@ -141,21 +238,37 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             break;                                                                 // sx:1942
         }
 
+        int key = -1, h1 = 0, cb = -1, ce = 0x7fffffff;
+        const bool narrow = K2_WARPS == 1 && A.k2_narrow && lim - j0 < 64;           // warp-uniform
+        if (narrow) {
+            if (lim - j0 < 32)
+                k2_narrow_row<GENERIC, 1>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
+            else
+                k2_narrow_row<GENERIC, 2>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
+            __syncwarp();                                                          // the row buffer is read by other lanes in the next row
+        } else {
         int carry = 0;            // f entering the first column of the round
         int hcarry = fc;          // h of the column left of the round
-        int key = -1;
-        for (int rbase = j0 & ~(K2_GROUP - 1); rbase <= lim; rbase += K2_GROUP * K2_WARPS) {
+        // rounds start at the window (rounded down to a lane's 8 columns), not at a 256-column boundary: the live window
+        // of a 1-10 kb PacBio-like task is ~200 columns wide (tools: 3.2 M rows, mean 203, 99 % below 384), and an aligned
+        // group would split about half of those rows into two rounds
+        for (int rbase = j0 & ~7; rbase <= lim; rbase += K2_GROUP * K2_WARPS) {
             const int gbase = rbase + K2_GROUP * warp;
             const bool active = gbase <= lim;                   // warp-uniform
             const int jl = gbase + 8 * lane;
             const int lo = j0 - jl, hi = lim - jl;              // columns k with lo <= k < hi are cells of this row
-            const bool full = (lo <= 0) && (hi >= 8);
+            const bool full = (lo < 0) && (hi >= 8);            // lo == 0: the lane holds the first live cell (its left neighbour is fc)
+            const int klo = imax(lo, 0), khi = imin(hi, 8);
+            const uint32_t livebits = khi > klo ? ((0xffu >> (8 - khi)) & (0xffu << klo)) : 0u;     // bit k: column jl + k is a cell of this row
             uint32_t wd[8];
             int hh[8], fl[8];
             int run = 0, fin0 = 0;
             if (active) {
-                const uint4 wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
-                const uint4 wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
+                uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
+                if (hi >= 0) {                                  // lanes right of the window read nothing (rounds are not 256-aligned:
+                    wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));          // their columns may lie past the row buffer)
+                    wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
+                }
                 wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
                 const uint32_t qw = (jl >> 3) < nqw ? qs[jl >> 3] : 0u;
                 const uint32_t x = GENERIC ? qw : (qw ^ trep);
@@ -165,8 +278,12 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                     const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
                     const int s = k2_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
                     hh[k] = add_max(M, s, e);                                          // sx:1797,1798
-                    int g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
-                    if (!full && !(k >= lo && k < hi)) g = 0;
+                    const int g = add_max_relu(hh[k], -oe_ins, 0);                     // sx:1863,1865 with h >= hh
+                    // Cells outside [j0, lim) are computed like the others and simply never looked at: columns left of j0
+                    // are dead (beg is monotone), columns right of lim are rewritten before they are read (every row
+                    // ends by writing its end slot), and F only flows to the right -- so the one thing to protect is the
+                    // F chain of the first live cell, which must start from zero.
+                    if (k == lo) run = 0;
                     fl[k] = run;
                     run = add_max(run, -e_ins, g);                                     // sx:1780,1781
                 }
@@ -217,10 +334,9 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                     h[k] = imax(hh[k], f);                                             // sx:1809
                     const int t = add_max_relu(h[k], -oe_del, 0);                      // sx:1866,1862
                     enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);        // {max(e-e_del,t), max(M-32768,0)=0}  sx:1770-1771
-                    if (full || (k >= lo && k < hi)) {
-                        key = imax(key, h[k] * 65536 + jl + k);                        // sx:1808,1816
-                        zbits |= (h[k] == 0 ? 1u : 0u) << k;
-                    }
+                    const int kk = h[k] * 65536 + jl + k;                              // sx:1808,1816
+                    key = imax(key, (livebits & (1u << k)) ? kk : -1);
+                    zbits |= (uint32_t)(1 - imin(h[k], 1)) << k;                       // cells outside the window are masked by the scan's ranges
                 }
                 if (K2_WARPS > 1 && lane == 31) xhl[warp] = h[7];
             }
@@ -229,41 +345,56 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 int hleft = __shfl_up_sync(0xffffffffu, h[7], 1);
                 if (lane == 0) hleft = (K2_WARPS == 1 || warp == 0) ? hcarry : xhl[warp - 1];
                 if (K2_WARPS == 1) hcarry = __shfl_sync(0xffffffffu, h[7], 31);
-                if (full) {
-                    // interior lane: columns jl..jl+7 are all cells of this row
-                    uint4 oa, ob;
-                    oa.x = enew[0] | (uint32_t)((lo == 0) ? fc : hleft);
-                    oa.y = enew[1] | (uint32_t)h[0]; oa.z = enew[2] | (uint32_t)h[1]; oa.w = enew[3] | (uint32_t)h[2];
-                    ob.x = enew[4] | (uint32_t)h[3]; ob.y = enew[5] | (uint32_t)h[4]; ob.z = enew[6] | (uint32_t)h[5]; ob.w = enew[7] | (uint32_t)h[6];
-                    *reinterpret_cast<uint4*>(eh + (jl & rm)) = oa;
-                    *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = ob;
-                } else {
-                    // boundary lane: store cells [lo,hi) and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
+                if (hi >= 0 && lo < 8) {
+                    // every lane that touches [j0, lim] stores its 8 words; a boundary lane patches two of them first:
+                    // the first cell's left neighbour is the first-column value fc, the end slot eh[lim] is {h1, 0}
+                    // (sx:1775,1904,1776); what lands left of j0 or right of lim is never read (see pass 1)
+                    uint32_t ow[8];
+                    ow[0] = enew[0] | (uint32_t)hleft;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (k >= lo && k <= hi) {
-                            const int h1 = (k == lo) ? fc : (k ? h[k - 1] : hleft);
-                            eh[(jl + k) & rm] = (k < hi ? enew[k] : 0u) | (uint32_t)h1;
+                    for (int k = 1; k < 8; ++k) ow[k] = enew[k] | (uint32_t)h[k - 1];
+                    if (!full) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (k == lo) ow[k] = (ow[k] & 0xffff0000u) | (uint32_t)fc;
+                            if (k == hi) ow[k] &= 0x0000ffffu;
                         }
                     }
+                    *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                    reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
                 }
-                reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
             }
             if (K2_WARPS > 1) hcarry = xhl[K2_WARPS - 1];      // only consumed when another round follows (then the last warp was active)
         }
         key = __reduce_max_sync(0xffffffffu, key);
         if (K2_WARPS > 1 && lane == 0) xkey[warp] = key;
         k2_sync<K2_WARPS>();                                               // (3) row buffer, zero bits and keys visible
-
-        // ---- row epilogue (identical in every thread of the CTA) ----
         if (K2_WARPS > 1) {
             key = xkey[0];
 #pragma unroll
             for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
         }
+        h1 = (int)(eh[lim & rm] & 0xffffu);
+        {
+            // narrowing scan (sx:1766-1769 / 1779,1782-1789): zero bit of cell c <-> eh[c+1].h == 0
+            const int mjw = key & 0xffff;
+            for (int wbase = (j0 >> 5); wbase <= ((lim - 1) >> 5); wbase += 32) {
+                const int wi = wbase + lane;
+                const uint32_t zw = (wi <= ((lim - 1) >> 5)) ? zb[wi & (rm >> 5)] : 0u;
+                const uint32_t za = zw & k2_range_mask(wi * 32, j0, mjw - 1);
+                const uint32_t ze = zw & k2_range_mask(wi * 32, mjw + 1, lim - 1);
+                if (za) cb = imax(cb, wi * 32 + 31 - __clz(za));
+                if (ze) ce = imin(ce, wi * 32 + __ffs(ze) - 1);
+            }
+            cb = __reduce_max_sync(0xffffffffu, cb);
+            ce = __reduce_min_sync(0xffffffffu, ce);
+        }
+        }   // general path
+
+        // ---- row epilogue (identical in every thread of the CTA) ----
         const int m = key >> 16, mj = key & 0xffff;
         cells += (unsigned long long)(lim - j0);
-        const int h1 = (int)(eh[lim & rm] & 0xffffu);
         if (lim == qlen) {                                                         // sx:1768,1913
             if (!(gscore > h1)) { max_ie = i; gscore = h1; }                       // sx:1941,1829,1831
         }
@@ -277,20 +408,9 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             if (di > dj) { if (max - m - (di - dj) * e_del > zdrop) break; }
             else         { if (max - m - (dj - di) * e_ins > zdrop) break; }
         }
-        // narrowing (sx:1766-1769 / 1779,1782-1789): zero bit of cell c <-> eh[c+1].h == 0
-        //   beg' = 2 + last zero cell in [j0, mj-1], else (fc == 0 ? j0+1 : j0)
-        //   end' = 1 + first zero cell in [mj+1, lim-1], else lim+1
-        int cb = -1, ce = 0x7fffffff;
-        for (int wbase = (j0 >> 5); wbase <= ((lim - 1) >> 5); wbase += 32) {
-            const int wi = wbase + lane;
-            const uint32_t zw = (wi <= ((lim - 1) >> 5)) ? zb[wi & (rm >> 5)] : 0u;
-            const uint32_t za = zw & k2_range_mask(wi * 32, j0, mj - 1);
-            const uint32_t ze = zw & k2_range_mask(wi * 32, mj + 1, lim - 1);
-            if (za) cb = imax(cb, wi * 32 + 31 - __clz(za));
-            if (ze) ce = imin(ce, wi * 32 + __ffs(ze) - 1);
-        }
-        cb = __reduce_max_sync(0xffffffffu, cb);
-        ce = __reduce_min_sync(0xffffffffu, ce);
+        // narrowing: beg' = 2 + last zero cell in [j0, mj-1], else (fc == 0 ? j0+1 : j0)
+        //            end' = 1 + first zero cell in [mj+1, lim-1], else lim+1
+        (void)mj;
         beg = cb >= 0 ? cb + 2 : (fc == 0 ? j0 + 1 : j0);
         end = ce != 0x7fffffff ? ce + 1 : lim + 1;
     }

@@ -139,6 +139,9 @@ static int bswref_extend_core_x(const bswref_params *p, int variant, int qlen, c
             f = f > t ? f : t;                                              /* sx:1968,1781 */
         }
         if (end > beg) ncell += end - beg;
+#ifdef BSWREF_ROWHIST
+        { extern long long bswref_rowhist[64]; int wdt = end > beg ? end - beg : 0; bswref_rowhist[wdt / 16 < 63 ? wdt / 16 : 63]++; }
+#endif
         eh[end].h = h1; eh[end].e = 0;                                      /* sx:1775,1904,1494-1495,1538 */
         if (j == qlen) {                                                    /* sx:1768,1913 */
             max_ie = gscore > h1 ? max_ie : i;                              /* sx:1941,1829 */
