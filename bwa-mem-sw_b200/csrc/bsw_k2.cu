@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         } else {
         int carry = 0;            // f entering the first column of the round
         int hcarry = fc;          // h of the column left of the round
+        // one warp, one round (the window fits 256 columns from j0 & ~7 -- nearly every row): the zero bits stay in
+        // registers and the narrowing below needs no pass over shared memory
+        const bool single = K2_WARPS == 1 && lim - (j0 & ~7) < K2_GROUP;
+        uint32_t zlast = 0;
         // rounds start at the window (rounded down to a lane's 8 columns), not at a 256-column boundary: the live window
         // of a 1-10 kb PacBio-like task is ~200 columns wide (tools: 3.2 M rows, mean 203, 99 % below 384), and an aligned
         // group would split about half of those rows into two rounds
@@ -353,17 +357,15 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                     ow[0] = enew[0] | (uint32_t)hleft;
 #pragma unroll
                     for (int k = 1; k < 8; ++k) ow[k] = enew[k] | (uint32_t)h[k - 1];
-                    if (!full) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            if (k == lo) ow[k] = (ow[k] & 0xffff0000u) | (uint32_t)fc;
-                            if (k == hi) ow[k] &= 0x0000ffffu;
-                        }
-                    }
                     *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-                    reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
+                    // the two patches are 16-bit stores behind the vector stores (same thread: ordered)
+                    unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
+                    if (lo > 0) eh16[2 * (j0 & rm)] = (unsigned short)fc;           // H half of column j0 (lo == 0: hleft already is fc)
+                    if (hi < 8) eh16[2 * (lim & rm) + 1] = 0;                       // E half of the end slot
+                    if (!single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
                 }
+                zlast = zbits;
             }
             if (K2_WARPS > 1) hcarry = xhl[K2_WARPS - 1];      // only consumed when another round follows (then the last warp was active)
         }
@@ -376,7 +378,14 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
         }
         h1 = (int)(eh[lim & rm] & 0xffffu);
-        {
+        if (single) {
+            // narrowing from the lanes' own zero bits (sx:1766-1769 / 1779,1782-1789): bit k of zlast <-> h of column jl + k is 0
+            const int mjw = key & 0xffff, jl = (j0 & ~7) + 8 * lane;
+            const uint32_t za = zlast & k2_range_mask(jl, j0, mjw - 1);
+            const uint32_t ze = zlast & k2_range_mask(jl, mjw + 1, lim - 1);
+            cb = __reduce_max_sync(0xffffffffu, za ? jl + 31 - __clz(za) : -1);
+            ce = __reduce_min_sync(0xffffffffu, ze ? jl + __ffs(ze) - 1 : 0x7fffffff);
+        } else {
             // narrowing scan (sx:1766-1769 / 1779,1782-1789): zero bit of cell c <-> eh[c+1].h == 0
             const int mjw = key & 0xffff;
             for (int wbase = (j0 >> 5); wbase <= ((lim - 1) >> 5); wbase += 32) {
