@@ -36,10 +36,38 @@ import numpy as np  # noqa: E402
 METRIC = "seed-extension GCUPS (cells_band; ksw_extend2 recurrence, bit-exact), tasks/s alongside"
 OPS_PER_CELL = 13            # 1 add, 4 sub, 7 max, 1 select
 FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum per bench step (1 M x 150 bp), one ncu capture of this command
-# (profiles/r01_dram_bytes_k0_k1.csv): K0 gather 174.5 MB read + 65.5 MB written, the eight K1 launches 93.2 MB read, 0 written
-# (the 32 MB of results stay in L2 until the D2H copy)
-NCU_TRAFFIC = {"k0": 240.0e6, "k1": 93.2e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per bench step (1 M x 150 bp) come from profiles/dram_traffic.json, written
+# from an ncu capture of this command (tools/ncu_traffic.py) together with the commit it was taken at; absent -> null
+
+
+def ncu_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+    except Exception:
+        return None
+
+
+def workload_config(args):
+    """The `config` object: identical in both arms (the driver compares it)."""
+    return {"workload": f"{args.workload}: {args.tasks} synthetic extension tasks per GPU per step (BASELINE.json configs[1] generator, "
+                        "tools/../csrc/synth.cpp, seed 1)",
+            "scoring": "a=1 b=4 o=6 e=1 w=100 zdrop=100 end_bonus=5", "variant": "V1 (RTL / BWA 0.7.8 recurrence)"}
+
+
+def native_oracle():
+    """The CPU baseline as BASELINE.md states it: the oracle compiled -O3 -march=native ON THIS BOX (the portable
+    libbswref.so that travels with the repo is x86-64-v2).  Falls back to the portable build if gcc is missing."""
+    import oracle as O
+    try:
+        out_dir = os.path.join(ROOT, "oracle", "_native")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "libbswref.so")
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-pthread", "-fPIC", "-std=c11", "-shared", "-o", so,
+                               os.path.join(ROOT, "oracle", "ksw_extend_ref.c")], stderr=subprocess.DEVNULL)
+        O.use_library(so)
+        return "gcc -O3 -march=native"
+    except Exception:
+        return "gcc -O3 -march=x86-64-v2 (portable build; native rebuild failed)"
 
 
 def parse_args():
@@ -115,6 +143,7 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     import oracle as O
+    flags = native_oracle()
     threads = O.max_threads()
     n = min(args.tasks, args.cpu_sample)
     times, cells = [], 0
@@ -127,13 +156,13 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32 (CPU port)", "data": "synthetic",
         "tasks_per_s": n * len(times) / total,
-        "config": {"workload": f"{args.workload}: {n} synthetic extension tasks per step (bounded sample of the {args.tasks}-task batch)",
-                   "scoring": "a=1 b=4 o=6 e=1 w=100 zdrop=100 end_bonus=5", "variant": "V1 (RTL / BWA 0.7.8 recurrence)"},
-        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port", "compiler": flags,
                          "sample": f"{n} tasks of {args.workload} per step, {len(times)} steps, oracle/ksw_extend_ref.c with {threads} pthreads "
-                                   "(the reference is Verilog RTL and cannot be built here)"},
+                                   "(the reference is Verilog RTL: it is pinned through a translated cycle model, oracle/_ref, which "
+                                   "runs ~1 M clocks/s and is no baseline)"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -244,6 +273,7 @@ def main():
     if rank == 0:
         steps = args.steps
         default_wl = args.workload == "cfg2_150bp" and n == 1_000_000
+        traffic = ncu_traffic()
         gcups = cells_all * steps / (dev_ms * 1e-3) * 1e-9
         e2e_gcups = cells_all * steps / e2e_s * 1e-9
         int_peak = peak["vimnmx_tops"]
@@ -257,13 +287,12 @@ def main():
         line = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16x2/int32", "data": "synthetic",
+            "dtype": "int16x2", "data": "synthetic",
             "tasks_per_s": n * world * steps / (dev_ms * 1e-3),
             "gcups_rect": rect_all * steps / (dev_ms * 1e-3) * 1e-9,    # qlen*tlen cells, for comparison with the literature
-            "config": {"workload": f"{args.workload}: {n} synthetic extension tasks per GPU per step (BASELINE.json configs[1] generator)",
-                       "scoring": "a=1 b=4 o=6 e=1 w=100 zdrop=100 end_bonus=5", "variant": "V1 (RTL / BWA 0.7.8 recurrence)",
-                       "l2": "256 MB flush write between timed steps", "cells_per_step_per_gpu": int(cells),
-                       "timing": "value = sum of CUDA-event durations of the kernel launches on the library stream; e2e = wall clock around the blocking C-ABI call"},
+            "config": workload_config(args),
+            "measurement": {"l2": "256 MB flush write between timed steps", "cells_per_step_per_gpu": int(cells),
+                            "timing": "value = sum of CUDA-event durations of the kernel launches on the library stream; e2e = wall clock around the blocking C-ABI call"},
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "gcups_rect": rect_all * steps / e2e_s * 1e-9,
                     "tasks_per_s": n * world * steps / e2e_s, "ms_per_step": e2e_s / steps * 1e3,
                     "h2d_bytes_per_step": int(st["h2d_bytes"] // steps), "d2h_bytes_per_step": int(st["d2h_bytes"] // steps),
@@ -272,19 +301,23 @@ def main():
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": int_peak, "unit": "Tops/s", "frac": achieved / int_peak,
-                         "traffic": NCU_TRAFFIC["k1"] if default_wl else None, "traffic_unit": "bytes of DRAM per step, K1 launches (ncu)",
+                         "frac_dpx": achieved / peak["dpx_tops"],
+                         "traffic": (traffic or {}).get("k1") if default_wl else None,
+                         "traffic_unit": "bytes of DRAM per step, K1 launches (ncu)", "traffic_capture": (traffic or {}).get("capture"),
                          "ops_per_cell": OPS_PER_CELL,
                          "peak_source": "bsw_measure_int_peak on this GPU: dependency-free VIMNMX stream (ALU pipe, where every max of the "
                                         "recurrence must issue); IADD3 %.2f, fused VIADDMNMX %.2f (2 ops/instr), IADD3+IMAD both pipes %.2f Tops/s at %.0f MHz"
                                         % (peak["iadd_tops"], peak["dpx_tops"], peak["dual_tops"], peak["sm_clock_mhz"])},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                             "traffic": (NCU_TRAFFIC["k0"] + NCU_TRAFFIC["k1"]) if default_wl else None, "algorithmic_bytes": alg_bytes,
-                             "traffic_unit": "bytes of DRAM per step, K0 + K1 launches (ncu, profiles/r01_dram_bytes_k0_k1.csv)",
+                             "traffic": ((traffic or {}).get("k0", 0) + (traffic or {}).get("k1", 0)) if (default_wl and traffic) else None,
+                             "algorithmic_bytes": alg_bytes, "traffic_unit": "bytes of DRAM per step, K0 + K1 launches (ncu)",
+                             "traffic_capture": (traffic or {}).get("capture"),
                              "peak_source": hbm_src,
                              "note": "streaming evidence only: the path is compute-bound at ~1e3 int-ops per byte"},
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle as O
+            flags = native_oracle()
             threads = O.max_threads()
             ns = min(n, args.cpu_sample)
             best = None
@@ -292,7 +325,7 @@ def main():
                 dt, c = cpu_oracle_run(args.workload, ns, 0, threads)
                 best = dt if best is None else min(best, dt)
             dt1, c1 = cpu_oracle_run(args.workload, min(ns, 20000), 0, 1)
-            line["cpu_baseline"] = {"value": c / best * 1e-9, "unit": "GCUPS", "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": c / best * 1e-9, "unit": "GCUPS", "cores": threads, "kind": "port", "compiler": flags,
                                     "tasks_per_s": ns / best, "single_thread_gcups": c1 / dt1 * 1e-9,
                                     "sample": f"first {ns} tasks of the same workload, best of 2, oracle/ksw_extend_ref.c with {threads} pthreads"}
         print(json.dumps(line), flush=True)

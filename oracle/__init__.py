@@ -50,10 +50,19 @@ ALN_DTYPE = np.dtype([("id", "<u4"), ("qb", "<i4"), ("qe", "<i4"), ("rb", "<i4")
 _lib = None
 
 
+def use_library(path: str) -> None:
+    """Load the oracle from another build of ksw_extend_ref.c (bench.py: the -march=native build made on the box)."""
+    global _lib, _LIB_PATH
+    _LIB_PATH = path
+    _lib = None
+    lib()
+
+
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if _LIB_PATH == os.path.join(_HERE, "libbswref.so"):
+            build()
         _lib = C.CDLL(_LIB_PATH)
         _lib.bswref_extend.restype = C.c_int
         _lib.bswref_extend.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.c_int,

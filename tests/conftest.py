@@ -16,7 +16,7 @@ def pytest_configure(config):
 def built():
     """Make sure the in-tree libraries exist (nvcc cross-compiles without a GPU)."""
     import __graft_entry__ as G
-    G.build()
+    G.build(force=False)
     return True
 
 

@@ -480,3 +480,45 @@ def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
         P2 = B.make_params2(B.make_params(**pk), w=w, pen_clip5=int(rng.integers(0, 8)), pen_clip3=int(rng.integers(0, 8)))
         want, _ = oracle_chain2aln(O, B, P2, seeds)
         assert_same(want, ctx.proc_element_batch(P2, seeds), "fused level 2")
+
+
+# ---------------------------------------------------------------- BASELINE configs at their full size, every task compared
+@pytest.mark.parametrize("name,n", [("cfg2_150bp", 1_000_000), ("cfg3_mixed", 1_000_000)])
+def test_full_size_every_task_every_field(B, O, ctx, name, n):
+    """BASELINE configs[1] / [2] at full size: all six outputs and the per-task cell count of ALL tasks against the oracle."""
+    both(B, O, ctx, B.synth_tasks(name, n, seed=1))
+
+
+@pytest.mark.parametrize("zdrop", [100, 400])
+def test_cfg4_all_long_reads(B, O, ctx, zdrop):
+    """BASELINE configs[3]: all 20 000 long-read extensions (1-10 kb, w = 500) on the intra-task kernel."""
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 20_000, seed=1), zdrop=zdrop)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_scores_at_the_16_bit_cap(B, O, ctx, variant):
+    """h0 = 32767 - qlen*max(mat): the packed 16x2 cell adds (a+b) before it subtracts b, i.e. it wraps inside the
+    intrinsic when M is within a+b of the cap; the admission rule promises exactness up to 32767."""
+    rng = np.random.default_rng(77)
+    qs, ts, h0 = [], [], []
+    for k in range(3000):
+        ql = int(rng.integers(1, 200))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        t = np.concatenate([q, rng.integers(0, 4, int(rng.integers(0, 30))).astype(np.uint8)])    # perfect match: the score climbs to the cap
+        if k % 3 == 1:
+            t[rng.integers(0, len(t), max(1, len(t) // 20))] = rng.integers(0, 4)
+        if k % 7 == 3:
+            q[int(rng.integers(0, ql))] = 4                                                           # N: matrix-lookup kernel
+        qs.append(q); ts.append(t); h0.append(32767 - ql * 1)
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.full(len(h0), 100, np.int32))
+    ro, _ = both(B, O, ctx, t, variant=variant, zdrop=0)
+    assert int(ro["score"].max()) == 32767
+    # a=2: max(mat) = 2
+    t["h0"] = np.array([32767 - 2 * len(q) for q in qs], np.int32)
+    ro, _ = both(B, O, ctx, t, variant=variant, a=2, b=3, zdrop=0)
+    assert int(ro["score"].max()) == 32767
+    t["h0"][5] += 1                                                                                   # one past the cap: rejected, not wrapped
+    with pytest.raises(B.BswError) as e:
+        ctx.sw_extend_batch(B.make_params(a=2, b=3, zdrop=0), t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    assert e.value.code == B.BSW_ERANGE
