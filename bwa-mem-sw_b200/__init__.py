@@ -373,6 +373,16 @@ def tbb_encode(params2: Params2, seeds) -> np.ndarray:
     return tbb
 
 
+def fpga_envelope(tbb_words):
+    """(tasks outside the FPGA's exact 8-bit envelope, index of the first one or -1) for a TBB image."""
+    tbb = np.ascontiguousarray(tbb_words, dtype=np.uint32)
+    n, first = C.c_int(0), C.c_int(-1)
+    rc = lib().bsw_fpga_envelope(tbb.ctypes.data, C.byref(n), C.byref(first))
+    if rc != BSW_OK:
+        raise BswError(rc, "bsw_fpga_envelope")
+    return n.value, first.value
+
+
 def rbb_decode(rbb_words, n: int) -> np.ndarray:
     rbb = np.ascontiguousarray(rbb_words, dtype=np.uint32)
     out = np.zeros(n, dtype=ALN_DTYPE)

@@ -133,6 +133,7 @@ struct bsw_ctx {
                                    // 0 never, 1 always, 2 auto (when there are at most 10 host threads per GPU)
     std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
+    bool fpga_strict = false;      // bsw_fpga_batch refuses (BSW_ERANGE) batches with a task outside the FPGA's 8-bit envelope
     bool k2_narrow = true;         // K2 rows below 64 columns run in registers (bsw_k2.cu::k2_narrow_row)
     bool device_plan = true;       // the chunk's sort + tile building run on the device (bsw_plan.cu); false: host build_plan
     bool fused_l2 = true;          // level 2 runs as one fused kernel (K3); false: host-orchestrated level-1 passes
@@ -1074,6 +1075,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "device_plan") { ctx->device_plan = value != 0; }
     else if (k == "k2_narrow") { ctx->k2_narrow = value != 0; }
+    else if (k == "fpga_strict") { ctx->fpga_strict = value != 0; }
     else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
@@ -1445,6 +1447,12 @@ int bsw_chain2aln_batch(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task*
 }
 
 void bsw_set_error_text(bsw_ctx* ctx, const char* text) { set_error(ctx, text ? text : ""); }
+int bsw_option_value(bsw_ctx* ctx, const char* key)
+{
+    if (!ctx || !key) return -1;
+    if (!strcmp(key, "fpga_strict")) return ctx->fpga_strict ? 1 : 0;
+    return -1;
+}
 
 // ---------------- async pair ----------------
 int bsw_submit(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tasks, size_t n, bsw_result* out, bsw_ticket* ticket)

@@ -85,6 +85,39 @@ int bsw_tbb_encode(const bsw_params2* P, const bsw_seed_task* tasks, size_t n, u
     return BSW_OK;
 }
 
+// The envelope in which the FPGA's 8-bit datapath is exact (oracle.rtl_envelope, checked against the
+// translated RTL in tests/test_rtl_pin.py and tests/test_rtl_width_model.py): per extension
+//   scores  h0 + qlen <= 127,  columns qlen <= 127,  first column h0 - o_del - e_del*tlen >= -128,
+//   first row h0 - o_ins - e_ins*qlen >= -128,  band 0 < w <= 63 (w << 1 is a signed 8-bit value in the second try).
+// The right extension starts from the left score, which is at most max(h0, init_score) + qlen_left.
+// *n_outside = tasks for which the FPGA may return something else than ksw_extend2 (this library returns ksw_extend2's
+// answer for them); *first_outside = index of the first one or -1.
+int bsw_fpga_envelope(const uint32_t* tbb, int* n_outside, int* first_outside)
+{
+    if (!tbb || !n_outside) return BSW_EINVAL;
+    *n_outside = 0;
+    if (first_outside) *first_outside = -1;
+    const size_t n = tbb[2];
+    if (n > (size_t)(BSW_RBB_WORDS / 5) || 8 + 8 * n > BSW_TBB_WORDS) return BSW_EWIRE;
+    const int o_del = (int)(tbb[0] & 0xff), e_del = (int)((tbb[0] >> 8) & 0xff), o_ins = (int)((tbb[0] >> 16) & 0xff), e_ins = (int)(tbb[0] >> 24);
+    const int w = (int)((tbb[1] >> 16) & 0xff);
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t* pw = tbb + 8 + 8 * i;
+        const int ql[2] = { (int)(pw[0] & 0xff), (int)(pw[1] & 0xff) }, tl[2] = { (int)((pw[0] >> 16) & 0x7ff), (int)((pw[1] >> 16) & 0x7ff) };
+        const int h0 = (int)(pw[4] & 0xff), init = (int)(int16_t)(pw[3] & 0xffff);
+        bool ok = w > 0 && w <= 63;
+        int h = h0;
+        for (int side = 0; side < 2 && ok; ++side) {
+            if (side == 1) h = ql[0] ? h0 + ql[0] : (init > h0 ? init : h0);          // upper bound of the left score
+            if (ql[side] == 0) continue;
+            ok = ql[side] <= 127 && h + ql[side] <= 127 && h > 0 && h - o_del - e_del * tl[side] >= -128 &&
+                 h - o_ins - e_ins * ql[side] >= -128;
+        }
+        if (!ok) { if (first_outside && *n_outside == 0) *first_outside = (int)i; ++*n_outside; }
+    }
+    return BSW_OK;
+}
+
 int bsw_rbb_decode(const uint32_t* rbb, size_t n, bsw_aln_record* out)
 {
     if (!rbb || (!out && n)) return BSW_EINVAL;
@@ -108,6 +141,15 @@ int bsw_fpga_batch(bsw_ctx* ctx, const uint32_t* tbb, uint32_t* rbb, int* n_resu
     const size_t n = tbb[2];                                                         // task_parse.v:944,697
     if (n > (size_t)(BSW_RBB_WORDS / 5) || 8 + 8 * n > BSW_TBB_WORDS) { bsw_set_error_text(ctx, "TBB: task count out of range"); return BSW_EWIRE; }
     if (n == 0) return BSW_OK;
+    if (bsw_option_value(ctx, "fpga_strict") > 0) {                                  // refuse what the FPGA itself cannot compute exactly
+        int outside = 0, first = -1;
+        const int rc = bsw_fpga_envelope(tbb, &outside, &first);
+        if (rc) return rc;
+        if (outside) {
+            bsw_set_error_text(ctx, ("TBB: " + std::to_string(outside) + " task(s) outside the FPGA's 8-bit envelope, first at index " + std::to_string(first)).c_str());
+            return BSW_ERANGE;
+        }
+    }
     bsw_params2 P;
     memset(&P, 0, sizeof(P));
     // the RTL's matrix is hard-wired: match +1, mismatch -4, N -1 (sw_pe_array_sw_extend.v:1915-1940)
@@ -141,6 +183,7 @@ int bsw_fpga_batch(bsw_ctx* ctx, const uint32_t* tbb, uint32_t* rbb, int* n_resu
         clamps[i].max_ins[1] = (int)(pw[6] & 0xffff); clamps[i].max_del[1] = (int)(pw[6] >> 16);   // proc_element.v:932-934
         s.id = pw[7];                                                                // proc_element.v:807
         const size_t nb = boff[i + 1] - boff[i];
+        if (nb > 2048) { bsw_set_error_text(ctx, "TBB: a task holds more than 2048 bases (query_mem, proc_element.v:347-350)"); return BSW_EWIRE; }
         const size_t dpos = 8 + 8 * n + ((size_t)pw[2] - off0);                      // task_parse.v:1924,1936
         if (pw[2] < off0 || dpos + (nb + 7) / 8 > BSW_TBB_WORDS) { bsw_set_error_text(ctx, "TBB: data offset out of range"); return BSW_EWIRE; }
         uint8_t* b = bases.data() + boff[i];

@@ -132,6 +132,11 @@ int bsw_chain2aln_batch(bsw_ctx *ctx, const bsw_params2 *params, const bsw_seed_
 int bsw_fpga_batch(bsw_ctx *ctx, const uint32_t *tbb_words, uint32_t *rbb_words, int *n_results);
 /* Helpers for hosts/tests that build or read the images (host side of the AFU contract). */
 int bsw_tbb_encode(const bsw_params2 *params, const bsw_seed_task *tasks, size_t n, uint32_t *tbb_words);
+/* How many tasks of the image lie outside the envelope in which the FPGA's 8-bit datapath equals ksw_extend2 (scores
+ * <= 127, flanks <= 127 bases, w <= 63, no wrap of the first column / first row generators: sw_pe_array_sw_extend.v:155-159,
+ * 1795,1975,770).  bsw_fpga_batch computes ksw_extend2's answer for those tasks, which the FPGA does
+ * not; with option "fpga_strict" = 1 it returns BSW_ERANGE instead.  first_outside may be NULL. */
+int bsw_fpga_envelope(const uint32_t *tbb_words, int *n_outside, int *first_outside);
 int bsw_rbb_decode(const uint32_t *rbb_words, size_t n, bsw_aln_record *out);
 
 /* ---------------- async pair (level 1) ---------------- */

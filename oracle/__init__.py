@@ -78,6 +78,8 @@ def lib():
         _lib.bswref_chain2aln_rtl.restype = None
         _lib.bswref_chain2aln_rtl.argtypes = [C.POINTER(Params2), C.POINTER(SeedTask), C.c_void_p, C.c_void_p,
                                               C.POINTER(C.c_int64)]
+        _lib.bswref_sw_extend_rtl8.restype = None
+        _lib.bswref_sw_extend_rtl8.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
         _lib.bswref_max_threads.restype = C.c_int
         _lib.bswref_clamp_w.restype = C.c_int
         _lib.bswref_clamp_w.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int]
@@ -130,6 +132,17 @@ def sw_extend_rtl(params: Params, query, target, h0: int, w: int, reg_score: int
     lib().bswref_sw_extend_rtl(C.byref(params), len(q), q.ctypes.data, len(t), t.ctypes.data, int(w), int(h0),
                                int(reg_score), int(max_ins), int(max_del), out.ctypes.data, C.byref(cells))
     return out, int(cells.value)
+
+
+def sw_extend_rtl8(query, target, h0, w, o_ins=6, e_ins=1, o_del=6, e_del=1, reg_score=0, max_ins=1000, max_del=1000):
+    """One sw_extend invocation at the RTL's widths (oracle/rtl_width_model.c): what the FPGA returns, wraps included.
+    int32[7] = score, aw, qle, tle, gtle, gscore, max_off.  Claimed for qlen <= 127 (see the file header)."""
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    out = np.zeros(7, dtype=np.int32)
+    lib().bswref_sw_extend_rtl8(len(q), q.ctypes.data, len(t), t.ctypes.data, int(o_ins), int(e_ins), int(o_del), int(e_del),
+                                int(w), int(h0), int(reg_score), int(max_ins), int(max_del), out.ctypes.data)
+    return out
 
 
 def rtl_envelope(qlen, tlen, h0, w, o_del=6, e_del=1, o_ins=6, e_ins=1) -> bool:

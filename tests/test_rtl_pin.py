@@ -206,3 +206,24 @@ def test_cuda_fpga_batch_equals_rtl(B, ctx):
         assert (mine[nw:] == 0).all()
         if n:
             assert_same(records_of(B, mine, n), records_of(B, rbb, n), "bsw_fpga_batch vs RTL")
+
+
+@pytest.mark.gpu
+def test_fpga_strict_refuses_what_the_fpga_cannot_compute(B, ctx):
+    """Option fpga_strict: a TBB with a task outside the 8-bit envelope is refused (BSW_ERANGE) instead of answered with
+    ksw_extend2's int32 result, which the FPGA would not return."""
+    q = np.zeros(60, np.uint8)
+    P2 = B.make_params2(B.make_params(zdrop=0), w=50, pen_clip5=5, pen_clip3=5)
+    ok = dict(q_left=q[:20], q_right=q[:30], t_left=q[:25], t_right=q[:35], init_score=19, qbeg=20, h0=19, id=1)
+    hot = dict(ok, h0=120, init_score=120, id=2)
+    ctx.set_option("fpga_strict", 1)
+    try:
+        rbb, n = ctx.pe_array_batch(B.tbb_encode(P2, [ok, ok]))
+        assert n == 2
+        with pytest.raises(B.BswError) as e:
+            ctx.pe_array_batch(B.tbb_encode(P2, [ok, hot]))
+        assert e.value.code == B.BSW_ERANGE and "index 1" in str(e.value)
+    finally:
+        ctx.set_option("fpga_strict", 0)
+    rbb, n = ctx.pe_array_batch(B.tbb_encode(P2, [ok, hot]))               # default: answered (ksw_extend2 semantics)
+    assert n == 2

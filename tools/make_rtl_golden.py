@@ -208,10 +208,33 @@ def run_level3():
                         n_words=np.array(nwords), clocks=np.array(clocks))
 
 
+# Known-answer tasks on which the two recurrence policies differ (tests/test_oracle_kat.py derives the answers by hand):
+# the RTL must give the V1 answer.  reg_score = the expected V1 score, so that sw_extend stops after one band try.
+KATS = [
+    dict(name="no_zero_guard", q=[0, 0], t=[0], h0=1, w=1, v1=(2, 1, 1, 1, 1, 0), v2=(2, 1, 1, 1, 0, 0)),
+    dict(name="first_column_unconditional", q=[0, 0, 0], t=[1, 1, 1, 0], h0=15, w=1, v1=(15, 0, 0, 4, 5, 0), v2=(15, 0, 0, 3, 3, 0)),
+    dict(name="narrowing_run_around_mj", q=[0, 0], t=[1, 1, 0, 0], h0=9, w=2, v1=(9, 0, 0, 2, 1, 0), v2=(9, 0, 0, 4, 3, 0)),
+]
+
+
+def run_kats():
+    rows = []
+    for k in KATS:
+        q, t = np.array(k["q"], np.uint8), np.array(k["t"], np.uint8)
+        mi = max_gap(len(q), 5, 6, 1)
+        out, _ = R.sw_extend(q, t, k["h0"], k["w"], reg_score=k["v1"][0], max_ins=mi, max_del=mi, scramble_seed=7)
+        rows.append(out)
+        print("kat", k["name"], "rtl", out)
+    np.savez_compressed(os.path.join(GOLD, "rtl_kat.npz"), names=np.array([k["name"] for k in KATS]), rtl=np.array(rows, np.int32))
+
+
 if __name__ == "__main__":
     if not R.available():
         sys.exit("oracle/_ref/librtlsim.so missing: run `make -C oracle` where /root/reference is mounted")
     os.makedirs(GOLD, exist_ok=True)
+    run_kats()
+    if "kat" in sys.argv[1:]:
+        sys.exit(0)
     if "l3" not in sys.argv[1:]:
         run_level1(level1_tasks(np.random.default_rng(11), 6000, wide=False), "rtl_sw_extend.npz")
         run_level1(level1_tasks(np.random.default_rng(12), 3000, wide=True), "rtl_sw_extend_wide.npz")
