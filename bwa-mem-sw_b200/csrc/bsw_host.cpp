@@ -12,6 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <future>
 #include <memory>
 #include <mutex>
@@ -124,7 +127,13 @@ struct TaskSource {
 
 struct bsw_ctx {
     std::vector<Device> devs;
-    std::vector<std::unique_ptr<Worker>> workers;
+    // Every batch call in flight owns a CallState (its worker pipelines: streams, pinned and device staging).  The FPGA
+    // keeps four batches in flight -- array k computes while k+1 is fetched (batch_manager.v:397-562, tbb.v:110-116) --
+    // so concurrent calls on one context must overlap, not queue: a call takes a free CallState (or makes one), runs
+    // without any context-wide lock, and puts it back.
+    struct CallState { std::vector<std::unique_ptr<Worker>> workers; };
+    std::vector<std::unique_ptr<CallState>> call_free, call_all;
+    std::mutex pool_mu;
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 16384;
@@ -145,9 +154,14 @@ struct bsw_ctx {
     std::string last_error;
     bsw_stats stats{};
     std::mutex async_mu;
-    struct Async { std::future<int> fut; uint32_t seq = 0; bool used = false; int status = 1; };
+    struct Async { uint32_t seq = 0; bool used = false, done = false; int status = 0; std::string error; };
     std::vector<Async> async;
     uint32_t async_seq = 0;
+    std::deque<std::pair<size_t, std::function<int()>>> async_queue;
+    std::condition_variable async_cv, async_done_cv;
+    std::vector<std::thread> async_threads;
+    bool async_stop = false;
+    void async_main();
 };
 
 struct bsw_resident {
@@ -161,8 +175,13 @@ struct bsw_resident {
 
 namespace {
 
+// The last error text is kept per calling thread (several threads may share a context); worker threads of a call
+// also write the context-wide copy, which the calling thread picks up when its call returns.
+thread_local std::string tl_last_error;
+
 void set_error(bsw_ctx* ctx, const std::string& s)
 {
+    tl_last_error = s;
     if (!ctx) return;
     std::lock_guard<std::mutex> g(ctx->err_mu);
     ctx->last_error = s;
@@ -726,22 +745,44 @@ void run_workers(size_t n, F& fn)
     if (helper.joinable()) helper.join();
 }
 
-Worker* get_worker(bsw_ctx* ctx, size_t k)
+void adopt_worker_error(bsw_ctx* ctx)
 {
-    while (ctx->workers.size() <= k) {
-        std::unique_ptr<Worker> w(new Worker());
-        w->dev = (int)(ctx->workers.size() % ctx->devs.size());      // workers are dealt round-robin over the devices
-        ctx->workers.push_back(std::move(w));
-    }
-    return ctx->workers[k].get();
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    tl_last_error = ctx->last_error;
 }
+
+Worker* get_worker(bsw_ctx* ctx, bsw_ctx::CallState& cs, size_t k)
+{
+    while (cs.workers.size() <= k) {
+        std::unique_ptr<Worker> w(new Worker());
+        w->dev = (int)(cs.workers.size() % ctx->devs.size());        // workers are dealt round-robin over the devices
+        cs.workers.push_back(std::move(w));
+    }
+    return cs.workers[k].get();
+}
+
+// RAII: a CallState for the duration of one batch call
+struct CallLease {
+    bsw_ctx* ctx; bsw_ctx::CallState* cs;
+    explicit CallLease(bsw_ctx* c) : ctx(c), cs(nullptr)
+    {
+        std::lock_guard<std::mutex> g(ctx->pool_mu);
+        if (!ctx->call_free.empty()) { cs = ctx->call_free.back().release(); ctx->call_free.pop_back(); }
+        else cs = new bsw_ctx::CallState();
+    }
+    ~CallLease()
+    {
+        std::lock_guard<std::mutex> g(ctx->pool_mu);
+        ctx->call_free.emplace_back(cs);
+    }
+};
 
 // The engine behind every batch entry point.  The batch is cut into chunks; `nworkers` host threads each run a
 // pipeline (fill -> validate -> plan -> pack -> H2D -> kernels -> D2H -> scatter) over the chunks they pull from a
 // shared counter, alternating between their two stream slots.  Workers are bound round-robin to the devices, so a
 // multi-GPU context balances dynamically -- the GPU analogue of task_parse handing the next task to the first PE
 // with room (sw_pe_array_task_parse.v:1600-1650).  No collective: results land in out[task].
-int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out,
+int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out,
                           uint32_t* cells, int force_kernel, std::vector<size_t>* overflow_out, std::vector<size_t>* rerun_n_out = nullptr)
 {
     const double w0 = now_ms();
@@ -803,7 +844,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     size_t nworkers = std::min<size_t>(max_workers, nchunks);
     if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
     if (nworkers < 1) nworkers = 1;
-    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
+    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, cs, k);
 
     // Fixed-size chunks pulled from a shared cursor.  Measured alternatives on 1 M x 150 bp, all slower: chunks that
     // shrink towards the end of the batch (shorter un-overlapped tail, but more launches and copies: 6.5 -> 7.0-9 ms)
@@ -822,7 +863,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     std::vector<size_t> overflow_all, rerun_all;
 
     auto worker_main = [&](size_t k) {
-        Worker& W = *ctx->workers[k];
+        Worker& W = *cs.workers[k];
         LocalStats st;
         std::vector<size_t> ovf, rrn;
         int r = 0;
@@ -904,6 +945,7 @@ int run_extensions_locked(bsw_ctx* ctx, const bsw_params* params, const TaskSour
     }
     if (overflow_out) overflow_out->swap(overflow_all);
     if (rerun_n_out) rerun_n_out->swap(rerun_all);
+    if (first_err.load()) adopt_worker_error(ctx);
     return first_err.load();
 }
 
@@ -919,9 +961,10 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
 {
     if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
     if (n == 0) return BSW_OK;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    CallLease lease(ctx);
+    bsw_ctx::CallState& cs = *lease.cs;
     std::vector<size_t> overflow, rerun_n;
-    int rc = run_extensions_locked(ctx, params, src, n, out, cells, -1, &overflow, &rerun_n);
+    int rc = run_extensions_locked(ctx, cs, params, src, n, out, cells, -1, &overflow, &rerun_n);
     if (rc) return rc;
     // K1R tasks whose live window outgrew the ring are rerun on K2, raw-mode tasks that hold an N on the staged path (which
     // classifies them for the matrix-lookup kernel): whole tasks, from scratch, results scattered over the first pass
@@ -932,7 +975,7 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
         const SubsetSrc sub{ &src, list.data() };
         std::vector<bsw_result> r2(list.size());
         std::vector<uint32_t> c2(cells ? list.size() : 0);
-        rc = run_extensions_locked(ctx, params, TaskSource{ &sub, fill_subset }, list.size(), r2.data(), cells ? c2.data() : nullptr,
+        rc = run_extensions_locked(ctx, cs, params, TaskSource{ &sub, fill_subset }, list.size(), r2.data(), cells ? c2.data() : nullptr,
                                    pass ? -1 : 2, nullptr);
         if (rc) return rc;
         for (size_t k = 0; k < list.size(); ++k) { out[list[k]] = r2[k]; if (cells) cells[list[k]] = c2[k]; }
@@ -1036,13 +1079,19 @@ int bsw_init(bsw_ctx** out, const int* device_ids, int n_devices, int streams_pe
 void bsw_destroy(bsw_ctx* ctx)
 {
     if (!ctx) return;
-    for (auto& a : ctx->async) if (a.used && a.fut.valid()) a.fut.wait();
+    {
+        std::unique_lock<std::mutex> g(ctx->async_mu);                    // queued batches still run; then the executor stops
+        ctx->async_stop = true;
+    }
+    ctx->async_cv.notify_all();
+    for (auto& th : ctx->async_threads) th.join();
     int prev = 0;
     cudaGetDevice(&prev);
-    for (auto& W : ctx->workers) {
-        cudaSetDevice(ctx->devs[(size_t)W->dev].id);
-        for (Slot& s : W->slots) { if (s.stream) cudaStreamSynchronize(s.stream); slot_free(s); }
-    }
+    for (auto& cs : ctx->call_free)
+        for (auto& W : cs->workers) {
+            cudaSetDevice(ctx->devs[(size_t)W->dev].id);
+            for (Slot& s : W->slots) { if (s.stream) cudaStreamSynchronize(s.stream); slot_free(s); }
+        }
     for (Device& D : ctx->devs) {
         cudaSetDevice(D.id);
         if (D.aux.stream) cudaStreamSynchronize(D.aux.stream);
@@ -1054,7 +1103,18 @@ void bsw_destroy(bsw_ctx* ctx)
     delete ctx;
 }
 
-const char* bsw_last_error(const bsw_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char* bsw_last_error(const bsw_ctx* ctx)
+{
+    if (!ctx) return "null context";
+    // this thread's own string (no other thread touches it); a failing call copies the text its workers left in the
+    // context-wide slot into it before it returns (adopt_worker_error)
+    if (tl_last_error.empty()) {
+        bsw_ctx* c = const_cast<bsw_ctx*>(ctx);
+        std::lock_guard<std::mutex> g(c->err_mu);
+        tl_last_error = c->last_error;
+    }
+    return tl_last_error.c_str();
+}
 
 int bsw_num_devices(const bsw_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
@@ -1238,7 +1298,8 @@ static int chain2aln_host(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_tas
 static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task* tasks, size_t n,
                            const bsw_seed_clamp* clamps, bsw_aln_record* out, std::vector<size_t>* leftover)
 {
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    CallLease lease(ctx);
+    bsw_ctx::CallState& cs = *lease.cs;
     const double call0 = now_ms();
     DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
     int rc = make_dev_params(ctx, &P->p, &dp, &sym, &fast_ok, &max_mat);
@@ -1272,7 +1333,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
     size_t nworkers = std::min<size_t>((size_t)opt.host_threads, nchunks);
     if (nworkers < ndev && nchunks >= ndev) nworkers = ndev;
     if (nworkers < 1) nworkers = 1;
-    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, k);
+    for (size_t k = 0; k < nworkers; ++k) get_worker(ctx, cs, k);
     std::atomic<size_t> next(0);
     std::atomic<int> first_err(0);
     std::atomic<uint64_t> launches(0), h2d(0), d2h(0), fused_seeds(0);
@@ -1376,7 +1437,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         return 0;
     };
     auto worker_main = [&](size_t k) {
-        Worker& W = *ctx->workers[k];
+        Worker& W = *cs.workers[k];
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
         if (!r && W.slots.size() < (size_t)ctx->slots_per_worker) {
@@ -1415,6 +1476,7 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
         ctx->stats.kernel_launches += launches.load(); ctx->stats.h2d_bytes += h2d.load(); ctx->stats.d2h_bytes += d2h.load();
         ctx->stats.tasks += fused_seeds.load();
     }
+    if (first_err.load()) adopt_worker_error(ctx);
     return first_err.load();
 }
 
@@ -1454,42 +1516,81 @@ int bsw_option_value(bsw_ctx* ctx, const char* key)
     return -1;
 }
 
-// ---------------- async pair ----------------
+// ---------------- async trio ----------------
+// "Write REQ_PEARRAY, poll the DSM busy bit" (batch_manager.v:347,851-854) with up to 16 tickets open.  Submitted
+// batches are queued to a small persistent executor (started by the first submit; BSW_ASYNC_THREADS, default 4 = the
+// FPGA's four PE arrays), each runs as an ordinary batch call on its own CallState, so up to four overlap on the GPU.
+// Ticket life: submit -> (poll)* -> wait.  bsw_poll never releases the ticket (0 = running, 1 = done, < 0 = failed);
+// bsw_wait blocks until the batch is done, returns its status, and releases the ticket -- always finish with it.
+void bsw_ctx::async_main()
+{
+    for (;;) {
+        std::function<int()> job; size_t slot = 0;
+        {
+            std::unique_lock<std::mutex> g(async_mu);
+            async_cv.wait(g, [&] { return async_stop || !async_queue.empty(); });
+            if (async_queue.empty()) return;                              // stop requested and nothing left to run
+            slot = async_queue.front().first; job = std::move(async_queue.front().second);
+            async_queue.pop_front();
+        }
+        const int rc = job();
+        std::string text = rc ? tl_last_error : std::string();
+        {
+            std::lock_guard<std::mutex> g(async_mu);
+            async[slot].status = rc; async[slot].error.swap(text); async[slot].done = true;
+        }
+        async_done_cv.notify_all();
+    }
+}
+
 int bsw_submit(bsw_ctx* ctx, const bsw_params* params, const bsw_task* tasks, size_t n, bsw_result* out, bsw_ticket* ticket)
 {
     if (!ctx || !ticket) return BSW_EINVAL;
     std::lock_guard<std::mutex> g(ctx->async_mu);
+    if (ctx->async_threads.empty()) {
+        const char* e = getenv("BSW_ASYNC_THREADS");
+        const int nt = e ? std::max(1, std::min(16, atoi(e))) : 4;
+        for (int k = 0; k < nt; ++k) ctx->async_threads.emplace_back([ctx]() { ctx->async_main(); });
+    }
     for (size_t k = 0; k < ctx->async.size(); ++k) {
         auto& a = ctx->async[k];
         if (a.used) continue;
-        a.used = true; a.seq = ++ctx->async_seq; a.status = 1;
+        a.used = true; a.done = false; a.seq = ++ctx->async_seq; a.status = 0; a.error.clear();
         const bsw_params pcopy = params ? *params : bsw_params{};
         const bool have_params = params != nullptr;
-        a.fut = std::async(std::launch::async, [=]() { return bsw_extend_batch(ctx, have_params ? &pcopy : nullptr, tasks, n, out); });
+        ctx->async_queue.emplace_back(k, [=]() { return bsw_extend_batch(ctx, have_params ? &pcopy : nullptr, tasks, n, out); });
         ticket->slot = (int32_t)k; ticket->seq = a.seq;
+        ctx->async_cv.notify_one();
         return BSW_OK;
     }
     set_error(ctx, "no free async slot");
     return BSW_EBUSY;
 }
 
-static int async_finish(bsw_ctx* ctx, const bsw_ticket* t, bool block)
+int bsw_poll(bsw_ctx* ctx, const bsw_ticket* t)
+{
+    if (!ctx || !t || t->slot < 0 || (size_t)t->slot >= ctx->async.size()) return BSW_EINVAL;
+    std::lock_guard<std::mutex> g(ctx->async_mu);
+    const auto& a = ctx->async[(size_t)t->slot];
+    if (!a.used || a.seq != t->seq) return BSW_EINVAL;
+    if (!a.done) return 0;
+    return a.status == BSW_OK ? 1 : a.status;
+}
+
+int bsw_wait(bsw_ctx* ctx, const bsw_ticket* t)
 {
     if (!ctx || !t || t->slot < 0 || (size_t)t->slot >= ctx->async.size()) return BSW_EINVAL;
     std::unique_lock<std::mutex> g(ctx->async_mu);
     auto& a = ctx->async[(size_t)t->slot];
     if (!a.used || a.seq != t->seq) return BSW_EINVAL;
-    if (!block && a.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return 0;
-    std::future<int> f = std::move(a.fut);
-    g.unlock();
-    const int rc = f.get();
-    g.lock();
+    const uint32_t seq = a.seq;
+    ctx->async_done_cv.wait(g, [&] { return a.done || !a.used || a.seq != seq; });
+    if (!a.used || a.seq != seq) return BSW_EINVAL;                       // another thread finished the same ticket first
+    const int rc = a.status;
+    if (rc) tl_last_error = a.error;
     a.used = false;
-    return block ? rc : (rc == BSW_OK ? 1 : rc);
+    return rc;
 }
-
-int bsw_poll(bsw_ctx* ctx, const bsw_ticket* ticket) { return async_finish(ctx, ticket, false); }
-int bsw_wait(bsw_ctx* ctx, const bsw_ticket* ticket) { return async_finish(ctx, ticket, true); }
 
 // ---------------- device-resident batches ----------------
 int bsw_resident_create(bsw_ctx* ctx, const bsw_params* params, const uint8_t* qbuf, const int64_t* qoff,

@@ -148,6 +148,73 @@ def test_task_record_layout_and_async(B, O, ctx):
     tk = ctx.submit(p, tasks, 500, out)
     ctx.wait(tk)
     assert_same(ro, out, "async")
+    # ticket life: submit -> poll until 1 -> wait (poll never releases the ticket; a second wait is refused)
+    out[:] = 0
+    tk = ctx.submit(p, tasks, 500, out)
+    import time
+    t0 = time.time()
+    while ctx.poll(tk) == 0 and time.time() - t0 < 30:
+        time.sleep(0.0005)
+    assert ctx.poll(tk) == 1 and ctx.poll(tk) == 1
+    ctx.wait(tk)
+    assert_same(ro, out, "async after polling")
+    with pytest.raises(B.BswError):
+        ctx.wait(tk)
+    # four tickets open at once (the FPGA's four PE arrays), each on its own slice
+    outs = [np.zeros(125, dtype=B.RESULT_DTYPE) for _ in range(4)]
+    tks = [ctx.submit(p, C.cast(C.byref(tasks, 125 * k * C.sizeof(B.Task)), C.POINTER(B.Task)), 125, outs[k]) for k in range(4)]
+    for tk in tks:
+        ctx.wait(tk)
+    assert_same(ro, np.concatenate(outs), "four async batches in flight")
+
+
+def test_four_threads_share_one_context(B, O, ctx):
+    """Concurrent blocking calls on ONE context overlap (no context-wide lock: every call takes its own set of worker
+    pipelines) and stay bit-exact; level 1, level 2 and level 3 mixed.  Each thread sees its own error text."""
+    import threading
+    t = B.synth_tasks("cfg3_mixed", 60_000, seed=90)
+    p, po = B.make_params(), O.make_params()
+    flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+    ro, _ = O.extend_batch(po, *flat)
+    seeds = seeds_from_flat(B.synth_tasks("cfg1_101bp", 1600, seed=91), 800, unset_score_every=4)
+    P2 = B.make_params2(B.make_params(zdrop=0), w=100, pen_clip5=5, pen_clip3=5)
+    want2, _ = oracle_chain2aln(O, B, P2, seeds)
+    tbb = B.tbb_encode(P2, seeds)
+    errs = []
+
+    def level1(k):
+        for _ in range(4):
+            r, _ = ctx.sw_extend_batch(p, *flat)
+            if not np.array_equal(r, ro):
+                errs.append(f"thread {k}: level 1 differs")
+
+    def level2(k):
+        for _ in range(6):
+            if not np.array_equal(ctx.proc_element_batch(P2, seeds), want2):
+                errs.append(f"thread {k}: level 2 differs")
+
+    def level3(k):
+        for _ in range(10):
+            rbb, n = ctx.pe_array_batch(tbb)
+            if n != 800 or not np.array_equal(B.rbb_decode(rbb, n), want2):
+                errs.append(f"thread {k}: level 3 differs")
+
+    def failing(k):
+        bad = t["h0"].copy(); bad[17] = 0
+        for _ in range(4):
+            try:
+                ctx.sw_extend_batch(p, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], bad, t["w"])
+                errs.append("an invalid batch was accepted")
+            except B.BswError as e:
+                if "task 17" not in str(e):
+                    errs.append(f"wrong error text in the failing thread: {e}")
+
+    th = [threading.Thread(target=f, args=(k,)) for k, f in enumerate((level1, level2, level3, failing, level1))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
 
 
 @pytest.mark.parametrize("path", L1, ids=[os.path.basename(p) for p in L1])
