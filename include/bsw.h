@@ -124,6 +124,26 @@ typedef struct { uint32_t id; int32_t qb, qe, rb, re, score, truesc, w; } bsw_al
 int bsw_chain2aln_batch(bsw_ctx *ctx, const bsw_params2 *params, const bsw_seed_task *tasks, size_t n,
                         bsw_aln_record *out);
 
+/* ---------------- host task builder: mem_chain2aln either side of the kernel ---------------- */
+/* What feeds param words 0-7 of a PE task (sw_pe_array_proc_element.v:815-934) from a read, a reference window and a
+ * chain of seeds -- host work in the (unmounted) quickassist port of BWA 0.7.8; restated from the published BWA-MEM
+ * algorithm (mem_chain2aln, cal_max_gap).  Coordinates: query positions in the read, rbeg in the 2*l_pac forward+reverse
+ * reference space, rseq = the reference bases of [rmax0, rmax1). */
+typedef struct { int32_t a, o_del, e_del, o_ins, e_ins, w; } bsw_chain_opt;       /* the mem_opt_t fields involved */
+typedef struct { int64_t rbeg; int32_t qbeg, len; } bsw_chain_seed;               /* mem_seed_t */
+typedef struct { int64_t rb, re; int32_t qb, qe, score, truesc, w, seedcov; } bsw_seed_aln;   /* the mem_alnreg_t fields the PE decides */
+/* rmax[0], rmax[1]: the reference span the chain's extensions may touch (flank + cal_max_gap either side, clipped to
+ * [0, 2*l_pac) and to the seed's side of the forward/reverse boundary). */
+int bsw_chain_window(const bsw_chain_opt *opt, int l_query, const bsw_chain_seed *seeds, int n, int64_t l_pac, int64_t rmax[2]);
+/* One bsw_seed_task per seed: left flanks reversed into `scratch` (bsw_seed_scratch_bytes gives a sufficient size), right
+ * flanks point into query / rseq; h0 = len * a; init_score = -1 with a left flank, len * a without; id = seed index. */
+size_t bsw_seed_scratch_bytes(int l_query, int64_t rmax0, int64_t rmax1, int n);
+int bsw_build_seed_tasks(const bsw_chain_opt *opt, const uint8_t *query, int l_query, const uint8_t *rseq, int64_t rmax0,
+                         int64_t rmax1, const bsw_chain_seed *seeds, int n, uint8_t *scratch, size_t scratch_bytes,
+                         bsw_seed_task *out);
+/* Record (relative to the seed, as the PE returns it) -> absolute coordinates, with BWA's rule for a seed without flanks. */
+void bsw_finish_seed(const bsw_chain_opt *opt, const bsw_chain_seed *seed, int l_query, const bsw_aln_record *rec, bsw_seed_aln *out);
+
 /* ---------------- level 3: FPGA wire format ---------------- */
 #define BSW_TBB_WORDS 65536   /* 4096 x 64 B (bwa_mem_sw.v:163-166) */
 #define BSW_RBB_WORDS 4096    /*  256 x 64 B (bwa_mem_sw.v:167-170) */
