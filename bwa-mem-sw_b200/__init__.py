@@ -434,8 +434,9 @@ def synth_cfg(name: str, seed: int = 1, n_frac: float = 0.0) -> SynthCfg:
     return c
 
 
-def synth_tasks(name: str, n: int, first: int = 0, seed: int = 1, n_frac: float = 0.0):
-    """Tasks [first, first+n) of a named workload: dict(qbuf,qoff,tbuf,toff,h0,w) in the flat level-1 layout."""
+def synth_tasks(name: str, n: int, first: int = 0, seed: int = 1, n_frac: float = 0.0, qbuf=None, tbuf=None):
+    """Tasks [first, first+n) of a named workload: dict(qbuf,qoff,tbuf,toff,h0,w) in the flat level-1 layout.
+    qbuf / tbuf: optional caller-owned uint8 buffers to fill (a streaming host reuses its registered batch buffers)."""
     S = synth_lib()
     cfg = synth_cfg(name, seed, n_frac)
     qlen = np.zeros(n, dtype=np.int32)
@@ -446,8 +447,9 @@ def synth_tasks(name: str, n: int, first: int = 0, seed: int = 1, n_frac: float 
     toff = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(qlen, out=qoff[1:])
     np.cumsum(tlen, out=toff[1:])
-    qbuf = np.zeros(int(qoff[-1]) + 8, dtype=np.uint8)
-    tbuf = np.zeros(int(toff[-1]) + 8, dtype=np.uint8)
+    if qbuf is None or tbuf is None or qbuf.size < int(qoff[-1]) + 8 or tbuf.size < int(toff[-1]) + 8:
+        qbuf = np.zeros(int(qoff[-1]) + 8, dtype=np.uint8)
+        tbuf = np.zeros(int(toff[-1]) + 8, dtype=np.uint8)
     S.bsw_synth_fill(C.byref(cfg), first, n, qoff.ctypes.data, toff.ctypes.data, qbuf.ctypes.data, tbuf.ctypes.data)
     w = np.full(n, cfg.w, dtype=np.int32)
     return dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=h0, w=w, n=n)

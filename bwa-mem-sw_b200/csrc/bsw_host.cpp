@@ -134,6 +134,7 @@ struct bsw_ctx {
     struct CallState { std::vector<std::unique_ptr<Worker>> workers; };
     std::vector<std::unique_ptr<CallState>> call_free, call_all;
     std::mutex pool_mu;
+    std::atomic<int> calls_live{ 0 };      // batch calls in flight: they share the host threads instead of each taking all
     int streams_per_device = 2;
     SchedOptions opt;
     size_t chunk_tasks = 16384;
@@ -766,12 +767,14 @@ struct CallLease {
     bsw_ctx* ctx; bsw_ctx::CallState* cs;
     explicit CallLease(bsw_ctx* c) : ctx(c), cs(nullptr)
     {
+        ctx->calls_live.fetch_add(1);
         std::lock_guard<std::mutex> g(ctx->pool_mu);
         if (!ctx->call_free.empty()) { cs = ctx->call_free.back().release(); ctx->call_free.pop_back(); }
         else cs = new bsw_ctx::CallState();
     }
     ~CallLease()
     {
+        ctx->calls_live.fetch_sub(1);
         std::lock_guard<std::mutex> g(ctx->pool_mu);
         ctx->call_free.emplace_back(cs);
     }
@@ -834,7 +837,9 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
     // The lean path leaves the host ~1 us per 1000 tasks of work, so what matters is the pipeline: every worker should own
     // several chunks, or all the copies are issued at once and nothing overlaps (32 host threads, one 31 k task chunk
     // each: 8.0 ms per 1 M tasks against 5.7 ms with 16 threads).  At most 8 workers per GPU, at least ~4 chunks each.
-    size_t max_workers = (size_t)opt.host_threads;
+    // calls in flight share the host: four concurrent calls with 32 threads each on a 32-core box just fight
+    const size_t live = (size_t)std::max(1, ctx->calls_live.load());
+    size_t max_workers = std::max<size_t>(ndev, (size_t)opt.host_threads / live);
     if (lean_mode) {
         max_workers = std::min<size_t>(max_workers, (lean_mode >= 2 ? 16 : 8) * ndev);
         const size_t share = n / (max_workers * 4);
