@@ -333,8 +333,8 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
                       : (L.kind == 3) ? k1p_launch(a, sym, st)
                       : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
-                      : (L.kind == 2 && k2_sub && (a.ring_cols = k2s_ring_cols(L.qmax, L.wmax)) > 0) ? k2s_launch(a, L.generic, st)
-                                      : k2_launch(a, L.generic, ctx->k2_warps, st);
+                      : (L.kind == 2 && k2_sub && variant == 1 && (a.ring_cols = k2s_ring_cols(L.qmax, L.wmax)) > 0) ? k2s_launch(a, L.generic, st)
+                                      : k2_launch(a, L.generic, ctx->k2_warps, variant, st);
         if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : (L.kind == 3 ? "K1P launch" : "K2 launch"));
         ++nl;
     }

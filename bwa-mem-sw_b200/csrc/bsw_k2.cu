@@ -150,7 +150,13 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
 
 template <int NW> __device__ __forceinline__ void k2_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 
-template <int GENERIC, int K2_WARPS>
+// VARIANT 1 = the RTL's recurrence, 2 = upstream BWA's (SURVEY appendix B "V2 deltas"): the zero guard on M, gap opens
+// taken from M, the first-column value only while beg == 0, and the zero-scan narrowing.  V2's narrowing can grow the
+// window past the cells the previous row wrote (end' = j + 2), so the next row reads a STALE slot of the row buffer --
+// whatever an older row, or the first-row fill, left there.  Two consequences here: boundary lanes store exactly the
+// cells [j0, lim] (V1 may scribble over the columns next to the window, nobody reads them), and in ring mode a column
+// that was never written is given its first-row value before the first row that can read it.
+template <int GENERIC, int K2_WARPS, int VARIANT>
 __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
 {
     constexpr int K2_NT = 32 * K2_WARPS;
@@ -221,6 +227,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     int beg = 0, end = qlen;                                                       // sx:769,779
     unsigned long long cells = 0;
     uint32_t tw = 0;
+    int hiw = rcap - 1;                  // V2: highest column whose slot holds its own (written or first-row) value
 
     for (int i = 0; i < tlen; ++i) {                                               // sx:1891
         if ((i & 7) == 0) tw = __ldg(tg + (i >> 3));                               // warp-uniform broadcast load
@@ -231,7 +238,14 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
 
         const int j0 = imax(beg, i - w);                                           // sx:1846,1894,1895,1803
         const int lim = imin(imin(end, i + w + 1), qlen);                          // sx:1980,1843,1897,1898,1842
-        const int fc = imax(h0 - (o_del + e_del * (i + 1)), 0);                    // V1: unconditional (sx:1796,1795,1880,1835,849)
+        const int fc = (VARIANT == 1 || j0 == 0) ? imax(h0 - (o_del + e_del * (i + 1)), 0) : 0;    // V1: unconditional (sx:1796,1795,1880,1835,849)
+        if (VARIANT == 2 && lim - 1 > hiw) {
+            // ring mode: columns the window reaches for the first time still hold what column - 2048 left there; a
+            // flat row buffer would show the first-row fill (sx:1975-1978) -- put it there
+            for (int c = hiw + 1 + tid; c <= lim - 1; c += K2_NT) eh[c & rm] = (uint32_t)(c > qlen ? 0 : imax(h0 - A.p.o_ins - c * e_ins, 0));
+            k2_sync<K2_WARPS>();
+        }
+        if (VARIANT == 2) hiw = imax(hiw, lim);
         if (lim <= j0) {
             // empty row: the reference's loop body never runs, h1 = fc, j stays at beg, m == 0 -> break
             if (j0 == qlen) { if (!(gscore > fc)) { max_ie = i; gscore = fc; } }   // sx:1768,1913,1941
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         }
 
         int key = -1, h1 = 0, cb = -1, ce = 0x7fffffff;
-        const bool narrow = K2_WARPS == 1 && A.k2_narrow && lim - j0 < 64;           // warp-uniform
+        const bool narrow = VARIANT == 1 && K2_WARPS == 1 && A.k2_narrow && lim - j0 < 64;           // warp-uniform
         if (narrow) {
             if (lim - j0 < 32)
                 k2_narrow_row<GENERIC, 1>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
@@ -251,7 +265,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         int hcarry = fc;          // h of the column left of the round
         // one warp, one round (the window fits 256 columns from j0 & ~7 -- nearly every row): the zero bits stay in
         // registers and the narrowing below needs no pass over shared memory
-        const bool single = K2_WARPS == 1 && lim - (j0 & ~7) < K2_GROUP;
+        const bool single = VARIANT == 1 && K2_WARPS == 1 && lim - (j0 & ~7) < K2_GROUP;
         uint32_t zlast = 0;
         // rounds start at the window (rounded down to a lane's 8 columns), not at a 256-column boundary: the live window
         // of a 1-10 kb PacBio-like task is ~200 columns wide (tools: 3.2 M rows, mean 203, 99 % below 384), and an aligned
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             const int klo = imax(lo, 0), khi = imin(hi, 8);
             const uint32_t livebits = khi > klo ? ((0xffu >> (8 - khi)) & (0xffu << klo)) : 0u;     // bit k: column jl + k is a cell of this row
             uint32_t wd[8];
-            int hh[8], fl[8];
+            int hh[8], fl[8], mk[VARIANT == 2 ? 8 : 1];
             int run = 0, fin0 = 0;
             if (active) {
                 uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
@@ -281,8 +295,15 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 for (int k = 0; k < 8; ++k) {
                     const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
                     const int s = k2_score<GENERIC>(GENERIC ? ((x >> (4 * k)) & 15u) : (x & (0xfu << (4 * k))), mat, mis, rlo, rhi);
-                    hh[k] = add_max(M, s, e);                                          // sx:1797,1798
-                    const int g = add_max_relu(hh[k], -oe_ins, 0);                     // sx:1863,1865 with h >= hh
+                    int g;
+                    if (VARIANT == 2) {
+                        mk[k] = M ? M + s : 0;                                         // V2: zero guard
+                        hh[k] = imax(mk[k], e);
+                        g = add_max_relu(mk[k], -oe_ins, 0);                           // V2: gap open from M
+                    } else {
+                        hh[k] = add_max(M, s, e);                                      // sx:1797,1798
+                        g = add_max_relu(hh[k], -oe_ins, 0);                           // sx:1863,1865 with h >= hh
+                    }
                     // Cells outside [j0, lim) are computed like the others and simply never looked at: columns left of j0
                     // are dead (beg is monotone), columns right of lim are rewritten before they are read (every row
                     // ends by writing its end slot), and F only flows to the right -- so the one thing to protect is the
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                     const int f = imax(fl[k], u);
                     u -= e_ins;
                     h[k] = imax(hh[k], f);                                             // sx:1809
-                    const int t = add_max_relu(h[k], -oe_del, 0);                      // sx:1866,1862
+                    const int t = add_max_relu(VARIANT == 2 ? mk[k] : h[k], -oe_del, 0);   // sx:1866,1862
                     enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);        // {max(e-e_del,t), max(M-32768,0)=0}  sx:1770-1771
                     const int kk = h[k] * 65536 + jl + k;                              // sx:1808,1816
                     key = imax(key, (livebits & (1u << k)) ? kk : -1);
@@ -357,12 +378,32 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                     ow[0] = enew[0] | (uint32_t)hleft;
 #pragma unroll
                     for (int k = 1; k < 8; ++k) ow[k] = enew[k] | (uint32_t)h[k - 1];
+                    if (VARIANT == 2 && !full) {
+                        // V2 boundary lane: exactly the cells [lo, hi) and the end slot, nothing beside them (stale slots are read later)
+                        uint32_t nz = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (k >= lo && k <= hi) {
+                                uint32_t v = (k == lo) ? ((ow[k] & 0xffff0000u) | (uint32_t)fc) : ow[k];
+                                if (k == hi) v &= 0x0000ffffu;
+                                eh[(jl + k) & rm] = v;
+                                nz |= (v != 0u ? 1u : 0u) << k;
+                            }
+                        }
+                        zbits = nz;
+                    } else {
                     *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
                     // the two patches are 16-bit stores behind the vector stores (same thread: ordered)
                     unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
                     if (lo > 0) eh16[2 * (j0 & rm)] = (unsigned short)fc;           // H half of column j0 (lo == 0: hleft already is fc)
                     if (hi < 8) eh16[2 * (lim & rm) + 1] = 0;                       // E half of the end slot
+                    if (VARIANT == 2) {                                             // V2 keeps "word != 0" bits per column (full lane: all eight are cells)
+                        zbits = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) zbits |= (ow[k] != 0u ? 1u : 0u) << k;
+                    }
+                    }
                     if (!single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
                 }
                 zlast = zbits;
@@ -385,6 +426,28 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             const uint32_t ze = zlast & k2_range_mask(jl, mjw + 1, lim - 1);
             cb = __reduce_max_sync(0xffffffffu, za ? jl + 31 - __clz(za) : -1);
             ce = __reduce_min_sync(0xffffffffu, ze ? jl + __ffs(ze) - 1 : 0x7fffffff);
+        } else if (VARIANT == 2) {
+            // BWA's zero scan over the stored words of columns [j0, lim]: cb = first non-zero column in [j0, lim-1],
+            // ce = last non-zero column in [beg', lim]; bit k of a lane's byte <-> the word of column jl + k is non-zero
+            int first = 0x7fffffff;
+            for (int wbase = (j0 >> 5); wbase <= (lim >> 5); wbase += 32) {
+                const int wi = wbase + lane;
+                const uint32_t zw = (wi <= (lim >> 5)) ? zb[wi & (rm >> 5)] : 0u;
+                const uint32_t za = zw & k2_range_mask(wi * 32, j0, lim - 1);
+                if (za) first = imin(first, wi * 32 + __ffs(za) - 1);
+            }
+            first = __reduce_min_sync(0xffffffffu, first);
+            const int nbeg = first != 0x7fffffff ? first : lim;
+            int last = -1;
+            for (int wbase = (nbeg >> 5); wbase <= (lim >> 5); wbase += 32) {
+                const int wi = wbase + lane;
+                const uint32_t zw = (wi <= (lim >> 5)) ? zb[wi & (rm >> 5)] : 0u;
+                const uint32_t ze = zw & k2_range_mask(wi * 32, nbeg, lim);
+                if (ze) last = imax(last, wi * 32 + 31 - __clz(ze));
+            }
+            last = __reduce_max_sync(0xffffffffu, last);
+            cb = nbeg;                                                             // carried to the common code below
+            ce = imin((last >= 0 ? last : nbeg - 1) + 2, qlen);
         } else {
             // narrowing scan (sx:1766-1769 / 1779,1782-1789): zero bit of cell c <-> eh[c+1].h == 0
             const int mjw = key & 0xffff;
@@ -420,6 +483,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         // narrowing: beg' = 2 + last zero cell in [j0, mj-1], else (fc == 0 ? j0+1 : j0)
         //            end' = 1 + first zero cell in [mj+1, lim-1], else lim+1
         (void)mj;
+        if (VARIANT == 2) { beg = cb; end = ce; continue; }
         beg = cb >= 0 ? cb + 2 : (fc == 0 ? j0 + 1 : j0);
         end = ce != 0x7fffffff ? ce + 1 : lim + 1;
     }
@@ -441,12 +505,12 @@ size_t k2_smem_bytes(int qmax, int wmax)
     return (size_t)K2_HDR_BYTES + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
 }
 
-template <int GENERIC, int NW>
+template <int GENERIC, int NW, int VARIANT>
 static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
 {
     if (!a.ntiles) return cudaSuccess;
     const size_t smem = k2_smem_bytes(a.qmax, a.wmax);
-    auto kern = k2_extend_kernel<GENERIC, NW>;
+    auto kern = k2_extend_kernel<GENERIC, NW, VARIANT>;
     // always the same (maximal) value: launches are issued concurrently from several host threads, and a per-launch
     // value would race with another thread's launch of the same kernel
     if (smem > 232448) return cudaErrorInvalidValue;
@@ -457,10 +521,11 @@ static cudaError_t k2_launch_t(const LaunchArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, cudaStream_t st)
+cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, int variant, cudaStream_t st)
 {
-    if (warps >= K2_MAXW) return generic ? k2_launch_t<1, 4>(a, st) : k2_launch_t<0, 4>(a, st);
-    return generic ? k2_launch_t<1, 1>(a, st) : k2_launch_t<0, 1>(a, st);
+    if (variant == 2) return generic ? k2_launch_t<1, 1, 2>(a, st) : k2_launch_t<0, 1, 2>(a, st);      // V2: one warp per task
+    if (warps >= K2_MAXW) return generic ? k2_launch_t<1, 4, 1>(a, st) : k2_launch_t<0, 4, 1>(a, st);
+    return generic ? k2_launch_t<1, 1, 1>(a, st) : k2_launch_t<0, 1, 1>(a, st);
 }
 
 }  // namespace bsw

@@ -51,8 +51,8 @@ size_t k1p_smem_bytes(int qmax, int nqw_max);
 cudaError_t k3_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
 size_t k3_smem_bytes(int qmax, int nqw_max);
 
-// K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  Variant 1 only.
-cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, cudaStream_t st);
+// K2: intra-task kernel (one warp per task, row-parallel with a prefix-max scan for F).  variant 1|2.
+cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, int variant, cudaStream_t st);
 size_t k2_smem_bytes(int qmax, int wmax);
 
 // K2S: K2's algorithm with 8 lanes per task, four long tasks per warp (narrow live windows), row ring of a.ring_cols

@@ -102,9 +102,22 @@ def test_edge_shapes(B, O, ctx):
     t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
     both(B, O, ctx, t)
     both(B, O, ctx, t, opts={"force_kernel": 2})
-    t2 = {k: (v[:-1] if k in ("h0", "w") else v) for k, v in t.items()}
-    t2["qoff"], t2["toff"] = t["qoff"][:-1], t["toff"][:-1]        # drop the 1537-long task: V2 is K1-only
-    both(B, O, ctx, t2, variant=2)
+    both(B, O, ctx, t, variant=2)                                    # 1536 / 1537: the K1 / K2 border under V2 as well
+    both(B, O, ctx, t, variant=2, opts={"force_kernel": 2})
+
+
+def test_v2_on_the_intra_task_kernel(B, O, ctx):
+    """Upstream-BWA semantics (V2) on K2: the zero guard, gap opens from M, the conditional first column and the
+    zero-scan narrowing with its stale row-buffer slots -- short tasks forced onto K2, then 1-10 kb reads (ring row
+    buffer), then other scorings and N bases."""
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 20_000, seed=6), variant=2, opts={"force_kernel": 2})
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=7, n_frac=0.01), variant=2, opts={"force_kernel": 2})
+    for zd in (100, 0):
+        both(B, O, ctx, B.synth_tasks("cfg4_long", 1500, seed=8), variant=2, zdrop=zd)
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 300, seed=9), variant=2, o_del=4, e_del=2, o_ins=7, e_ins=1)
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=10), variant=2, opts={"force_kernel": 2}, a=2, b=3, zdrop=20)
+    from helpers import random_small_tasks
+    both(B, O, ctx, random_small_tasks(np.random.default_rng(11), 6000), variant=2, opts={"force_kernel": 2})
 
 
 def test_empty_batch_and_errors(B, ctx):
