@@ -113,7 +113,6 @@ struct LaunchArgs {
     int32_t          qmax;         // max qlen over the launch (sizes the per-lane row buffer)
     int32_t          nqw_max;      // max query words per lane over the launch (K1)
     int32_t          wmax;         // max band over the launch (K2: decides whether the row buffer may be a ring)
-    int32_t          ring_cols;    // K2S: columns of the per-task row ring (power of two)
     int32_t          k2_narrow;    // K2: rows narrower than 64 columns take the register-only path (option "k2_narrow", default 1)
     // lean output (flat batches planned on the device): the final 24-byte record {score,qle,tle,gtle,gscore,max_off} at
     // out24[out_index[slot]] -- task order, ready for one D2H into the caller's array -- the cell count in cells_out (may

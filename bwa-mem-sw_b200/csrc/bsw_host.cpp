@@ -307,7 +307,7 @@ int make_dev_params(bsw_ctx* ctx, const bsw_params* p, DevParams* dp, int* sym, 
 // Host statistics accumulated by one worker and merged once per call.
 struct LocalStats { double pack_ms = 0, validate_ms = 0, kernel_ms = 0; uint64_t h2d = 0, d2h = 0, launches = 0, tasks = 0, cells = 0, packed_chunks = 0, raw_chunks = 0; };
 
-int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, bool k2_sub, const uint32_t* out_index)
+int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int variant, bool count_cells, size_t* nlaunch, const uint32_t* out_index)
 {
     const Plan& P = s.plan;
     size_t nl = 0;
@@ -331,11 +331,9 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
-                      : (L.kind == 3) ? k1p_launch(a, sym, st)
                       : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
-                      : (L.kind == 2 && k2_sub && variant == 1 && (a.ring_cols = k2s_ring_cols(L.qmax, L.wmax)) > 0) ? k2s_launch(a, L.generic, st)
                                       : k2_launch(a, L.generic, ctx->k2_warps, variant, st);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : (L.kind == 3 ? "K1P launch" : "K2 launch"));
+        if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : "K2 launch");
         ++nl;
     }
     if (spread) {
@@ -368,7 +366,7 @@ int enqueue_gather(bsw_ctx* ctx, Slot& s)
 // (long tasks, bad lengths, ...) goes through the staged path, which also words the error messages.
 bool raw_chunk_eligible(const ExtTask* t, size_t count, int max_mat, const SchedOptions& opt)
 {
-    if (opt.force_kernel == 2 || opt.pair || count == 0) return false;
+    if (opt.force_kernel == 2 || count == 0) return false;
     const uint8_t* q0 = t[0].q; const uint8_t* t0 = t[0].t;
     if (!q0 || !t0) return false;
     for (size_t i = 0; i < count; ++i) {
@@ -489,7 +487,7 @@ int slot_submit(bsw_ctx* ctx, Slot& s, size_t first, size_t count, int max_mat, 
         if (e != cudaSuccess) return cuda_fail(ctx, e, "device planner launch");
     }
     if ((rc = enqueue_gather(ctx, s))) return rc;
-    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, opt.k2_sub, s.d_oidx()))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, false, &s.nlaunch, s.d_oidx()))) return rc;
     if (s.dp_mode) s.nlaunch += 3;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, count * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
@@ -520,7 +518,7 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
                      bool packed2, std::vector<size_t>* rerun_n)
 {
     const double t0 = now_ms();
-    if (opt.force_kernel == 2 || opt.pair || opt.ring || count == 0) return 1;
+    if (opt.force_kernel == 2 || opt.ring || count == 0) return 1;
     int rc;
     const size_t max_tiles = count / TILE_LANES + 8;
     const size_t off_param = 0, off_src = count * sizeof(SlotParam);
@@ -625,7 +623,7 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
         if (e != cudaSuccess) return cuda_fail(ctx, e, "device planner launch");
     }
     if ((rc = enqueue_gather(ctx, s))) return rc;
-    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, true, &s.nlaunch, false, s.d_oidx()))) return rc;
+    if ((rc = enqueue_launches(ctx, s, dp, sym, opt.variant, true, &s.nlaunch, s.d_oidx()))) return rc;
     if (timing) CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_registered ? (void*)(out + first) : (void*)s.h_out24, s.d_out24, count * sizeof(bsw_result),
                                   cudaMemcpyDeviceToHost, s.stream));
@@ -793,7 +791,7 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
     int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
     if (rc) return rc;
     SchedOptions opt = ctx->opt;
-    if (force_kernel >= 0) { opt.force_kernel = force_kernel; opt.k2_sub = false; }      // the overflow rerun: plain K2
+    if (force_kernel >= 0) opt.force_kernel = force_kernel;                              // the overflow rerun: plain K2
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
@@ -1134,14 +1132,12 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "slots") { if (value < 1 || value > 16) return BSW_EINVAL; ctx->slots_per_worker = (int)value; }
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
-    else if (k == "k2_sub") { ctx->opt.k2_sub = value != 0; }
     else if (k == "k2_warps") { if (value != 1 && value != 4) return BSW_EINVAL; ctx->k2_warps = (int)value; }
     else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "device_plan") { ctx->device_plan = value != 0; }
     else if (k == "k2_narrow") { ctx->k2_narrow = value != 0; }
     else if (k == "fpga_strict") { ctx->fpga_strict = value != 0; }
-    else if (k == "k1_pair") { ctx->opt.pair = value != 0; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
     else { set_error(ctx, "unknown option " + k); return BSW_EINVAL; }
@@ -1653,7 +1649,7 @@ int bsw_resident_run(bsw_ctx* ctx, bsw_resident* R, double* kernel_ms, uint64_t*
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k0, s.stream));
     size_t nl = 0;
     { int rc = enqueue_gather(ctx, s);                  // the device half of the scheduler is part of every pass
-      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl, ctx->opt.k2_sub, nullptr);
+      if (!rc) rc = enqueue_launches(ctx, s, R->dp, R->sym, R->variant, true, &nl, nullptr);
       if (rc) { cudaSetDevice(prev); return rc; }
       if (s.plan.n_k1_tiles) ++nl; }
     CUDA_TRY(ctx, cudaEventRecord(s.ev_k1, s.stream));

@@ -42,10 +42,6 @@ size_t k1_smem_bytes(int qmax, int nqw_max);
 // K1R: K1's lane function over a 512-column ring for long tasks (V1); overflowing tasks come back with STATUS_OVERFLOW.
 cudaError_t k1r_launch(const LaunchArgs& a, int generic, int sym, cudaStream_t st);
 
-// K1P: two tasks per lane, int16x2-packed scores (V1 recurrence, match/mismatch scoring).  a.tiles = (A, B) tile pairs.
-cudaError_t k1p_launch(const LaunchArgs& a, int sym, cudaStream_t st);
-size_t k1p_smem_bytes(int qmax, int nqw_max);
-
 // K3: fused seed-task kernel (level 2 on the device): left + right extension, band retry, clip, record.
 // a.tiles = (left, right) tile pairs, a.seeds[pair*32+lane], a.out[pair*32+lane] = bsw_aln_record.
 cudaError_t k3_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
@@ -55,10 +51,6 @@ size_t k3_smem_bytes(int qmax, int nqw_max);
 cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, int variant, cudaStream_t st);
 size_t k2_smem_bytes(int qmax, int wmax);
 
-// K2S: K2's algorithm with 8 lanes per task, four long tasks per warp (narrow live windows), row ring of a.ring_cols
-// columns; tasks whose window outgrows the ring come back with STATUS_OVERFLOW (the host reruns them on K2).
-cudaError_t k2s_launch(const LaunchArgs& a, int generic, cudaStream_t st);
-int k2s_ring_cols(int qmax, int wmax);
 
 // INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
 // streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.

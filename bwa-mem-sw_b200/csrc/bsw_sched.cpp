@@ -125,10 +125,6 @@ static inline size_t k1_tile_smem(int qmax, int nqw)
 {
     return 128 + ((size_t)(nqw + 8) + (size_t)(qmax + 1 + K1_EH_SLACK)) * TILE_LANES * 4u;
 }
-static inline size_t k1p_tile_smem(int qmax, int nqw)
-{
-    return 128 + (size_t)2 * (size_t)(nqw + 8) * TILE_LANES * 4u + (size_t)(qmax + 1 + K1_EH_SLACK) * TILE_LANES * 8u;
-}
 static inline size_t k2_task_smem(int qmax, int wmax)
 {
     const size_t qcap = ((size_t)qmax + 1 + 255) & ~(size_t)255;
@@ -217,14 +213,13 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
         while (cend < n && (key[order[cend]] >> class_shift) == c) ++cend;
         const bool is_k2 = c >= 4u;
         const bool is_ring = (c & 6u) == 2u;
-        const bool is_pair = c == 0u && opt.pair && opt.variant == 1;
         Launch L{};
-        L.kind = is_k2 ? 2 : (is_ring ? 4 : (is_pair ? 3 : 1)); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
+        L.kind = is_k2 ? 2 : (is_ring ? 4 : 1); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
         int occ0 = 0;
         while (i < cend) {
-            // one K2 task, one K1 tile of 32 tasks, or one K1P pair of tiles (64 tasks: lane l = tasks 2l and 2l+1)
-            const size_t ntask = is_k2 ? 1 : std::min<size_t>(is_pair ? 2 * TILE_LANES : TILE_LANES, cend - i);
-            const int nsub = is_pair ? 2 : 1;
+            // one K2 task or one K1 tile of 32 tasks
+            const size_t ntask = is_k2 ? 1 : std::min<size_t>(TILE_LANES, cend - i);
+            const int nsub = 1;
             TileHdr hd[2];
             int qmax = 0, nqw_max = 0, wmax = 0;
             for (int sub = 0; sub < nsub; ++sub) {
@@ -232,7 +227,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                 hd[sub].slot0 = (uint32_t)plan->slots.size();
                 int tq = 0, tt = 0;
                 const size_t lanes = is_k2 ? 1 : (size_t)TILE_LANES;
-                if (!is_pair && ntask == lanes) {
+                if (ntask == lanes) {
                     // a full tile (the common case): write the 32 slots through raw pointers
                     const size_t s0 = plan->slots.size();
                     plan->slots.resize(s0 + lanes); plan->slot_src.resize(s0 + lanes); plan->slot_task.resize(s0 + lanes);
@@ -251,7 +246,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                     plan->est_cells += cells;
                 } else
                 for (size_t l = 0; l < lanes; ++l) {
-                    const size_t k = is_pair ? 2 * l + (size_t)sub : l;
+                    const size_t k = l;
                     if (k < ntask) {
                         const uint32_t ti = order[i + k];
                         const ExtTask& t = tasks[ti];
@@ -282,7 +277,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                 hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16) | (planes ? TILE_ONEHOT : 0u);
                 qmax = std::max(qmax, tq); nqw_max = std::max(nqw_max, nqw);
             }
-            const size_t smem = is_ring ? (size_t)K1R_RING * TILE_LANES * 4u : is_k2 ? k2_task_smem(qmax, wmax) : (is_pair ? k1p_tile_smem(qmax, nqw_max) : k1_tile_smem(qmax, nqw_max));
+            const size_t smem = is_ring ? (size_t)K1R_RING * TILE_LANES * 4u : is_k2 ? k2_task_smem(qmax, wmax) : k1_tile_smem(qmax, nqw_max);
             // bucket boundary: start a new launch when this tile would fit at >= 1.3x the occupancy of the launch
             const int occ = occupancy(smem);
             L.wmax = std::max(L.wmax, wmax);
@@ -302,7 +297,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
 
 bool build_dp_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g)
 {
-    if (n == 0 || opt.pair || opt.ring) return false;
+    if (n == 0 || opt.ring) return false;
     DpBuckets bks;
     memset(&bks, 0, sizeof(bks));
     for (size_t i = 0; i < n; ++i) {
@@ -316,7 +311,7 @@ bool dp_geometry(const DpBuckets& bks, size_t n, const SchedOptions& opt, Plan* 
 {
     plan->tiles.clear(); plan->slots.clear(); plan->slot_src.clear(); plan->slot_task.clear(); plan->launches.clear();
     plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
-    if (n == 0 || opt.pair || opt.ring) return false;
+    if (n == 0 || opt.ring) return false;
     const DpBuckets::B (*bk)[128] = bks.bk;
     static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
     const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : (n >= 100000 ? 130 : 200));

@@ -31,12 +31,8 @@ struct SchedOptions {
     int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
     int host_threads = 0;       // 0 = hardware concurrency (capped)
     bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
-    bool k2_sub = false;        // long tasks first run on K2S (8 lanes per task, small row ring; overflows rerun on K2).
-                                // Off by default: measured slower than K2 (the four sub-warps of a warp do not stay converged)
     bool ring = false;          // long V1 tasks whose first row fits run on K1R (ring row buffer in K1's lane function).
                                 // Off by default: measured slower than K2 (3 warps/SM with a 512-column ring), see DESIGN.md
-    bool pair = false;          // V1 + FAST tasks run two per lane (K1P, packed int16x2).  Off by default: measured slower
-                                // than K1 on B200 (occupancy halves with the doubled row buffer), see DESIGN.md section 5
 };
 
 constexpr int K1_QLEN_CAP = 1536;        // shared-memory limit of one K1 tile (227 KB / (32 lanes * 4.5 B per column))
@@ -44,7 +40,7 @@ constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
 constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
 
 struct Launch {
-    int kind;          // 1 = K1, 2 = K2, 4 = K1R (long tasks, ring row buffer), 3 = K1P (tiles come in pairs: A tile, B tile), 5 = K3 (pairs: left tile, right tile)
+    int kind;          // 1 = K1, 2 = K2, 4 = K1R (long tasks, ring row buffer), 5 = K3 (pairs: left tile, right tile)
     int generic;       // 1 = matrix lookup scoring
     uint32_t tile0, ntiles;
     int qmax, nqw_max;

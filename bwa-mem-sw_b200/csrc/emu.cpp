@@ -14,7 +14,6 @@
 #include "../../include/bsw.h"
 #include "bsw_device.cuh"
 #include "bsw_k1_core.cuh"
-#include "bsw_k1p_core.cuh"
 #include "bsw_k3_core.cuh"
 #include "bsw_sched.h"
 
@@ -53,28 +52,6 @@ void run_ring_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slot
     }
 }
 
-template <int SYM>
-void run_pair(const DevParams& dp, const TileHdr& ha, const TileHdr& hb, const SlotParam* slots, const uint32_t* arena,
-              SlotResult* out, int qmax, int nqw_max)
-{
-    const int nqa = (int)(ha.nqw_ntw & 0x7fffu), nqb = (int)(hb.nqw_ntw & 0x7fffu);
-    const size_t qwords = (size_t)(nqw_max + K1_QS_EXTRA) * K1_S;
-    std::vector<uint32_t> qsa(qwords, 0xdeadbeefu), qsb(qwords, 0xdeadbeefu);
-    std::vector<uint32_t> eh((size_t)(qmax + 1 + K1_EH_SLACK) * K1P_CS, 0xdeadbeefu);
-    memcpy(qsa.data(), arena + (size_t)ha.qoff16 * 4, (size_t)nqa * K1_S * 4);
-    memcpy(qsb.data(), arena + (size_t)hb.qoff16 * 4, (size_t)nqb * K1_S * 4);
-    for (int lane = 0; lane < K1_S; ++lane) {
-        const SlotParam& spa = slots[ha.slot0 + lane];
-        const SlotParam& spb = slots[hb.slot0 + lane];
-        if (spa.qlen <= 0 && spb.qlen <= 0) continue;
-        SlotResult ra, rb;
-        k1p_pair<SYM>(dp, spa, spb, nqa, nqb, eh.data() + 2 * lane, qsa.data() + lane, qsb.data() + lane,
-                      arena + (size_t)ha.toff16 * 4 + lane, arena + (size_t)hb.toff16 * 4 + lane, ra, rb);
-        if (spa.qlen > 0) out[ha.slot0 + lane] = ra;
-        if (spb.qlen > 0) out[hb.slot0 + lane] = rb;
-    }
-}
-
 // Host restatement of the k0 gather kernel (bsw_k0.cu): lane l of a K1 tile copies its task's packed words from the
 // task-major source arena into the tile-interleaved block.
 void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
@@ -108,10 +85,9 @@ void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
 extern "C" {
 
 // info[0] = launches, info[1] = tiles, info[2] = arena words, info[3] = padded lanes
-int bsw_emu_pair = 0;
 int bsw_emu_force_kernel = 1;   // 1: everything on K1; 0: auto (long tasks -> K1R; tasks that need K2 make the call fail)
 int bsw_emu_k2_min_qlen = 384;
-int bsw_emu_ring = 0;           // 1: long tasks go to K1R (the ring-buffer lane function)      // tests flip this to exercise K1 (one task per lane) and K1P (two per lane)
+int bsw_emu_ring = 0;           // 1: long tasks go to K1R (the ring-buffer lane function)
 
 int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8_t* qbuf, const int64_t* qoff,
                               const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
@@ -137,7 +113,7 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
     const int sym = (params->o_del == params->o_ins && params->e_del == params->e_ins) ? 1 : 0;
 
     SchedOptions opt;
-    opt.variant = variant; opt.force_kernel = bsw_emu_force_kernel; opt.fast_matrix = fast; opt.host_threads = 4; opt.pair = bsw_emu_pair != 0;
+    opt.variant = variant; opt.force_kernel = bsw_emu_force_kernel; opt.fast_matrix = fast; opt.host_threads = 4;
     opt.k2_min_qlen = bsw_emu_k2_min_qlen; opt.ring = bsw_emu_ring != 0;
     std::vector<ExtTask> v(n);
     for (size_t i = 0; i < n; ++i) {
@@ -160,13 +136,6 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
     gather_host(P, src.data(), arena.data());
     std::vector<SlotResult> res(P.slots.size());
     for (const Launch& L : P.launches) {
-        if (L.kind == 3) {
-            for (uint32_t t = L.tile0; t + 1 < L.tile0 + L.ntiles; t += 2) {
-                if (sym) run_pair<1>(dp, P.tiles[t], P.tiles[t + 1], P.slots.data(), arena.data(), res.data(), L.qmax, L.nqw_max);
-                else     run_pair<0>(dp, P.tiles[t], P.tiles[t + 1], P.slots.data(), arena.data(), res.data(), L.qmax, L.nqw_max);
-            }
-            continue;
-        }
         if (L.kind == 4) {
             for (uint32_t t = L.tile0; t < L.tile0 + L.ntiles; ++t) {
                 if (L.generic) { if (sym) run_ring_tile<1, 1>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); else run_ring_tile<1, 0>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); }

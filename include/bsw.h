@@ -54,11 +54,15 @@ void bsw_destroy(bsw_ctx *ctx);
 const char *bsw_last_error(const bsw_ctx *ctx);          /* thread-unsafe convenience: last error text of this ctx */
 const char *bsw_version(void);
 /* Options (all optional): "variant" {1,2}; "host_threads" N; "chunk_tasks" N (pipeline granularity, default 16384);
- * "slots" N (chunks one host worker keeps in flight, default 2); "raw_inputs" {0 never, 1 always, 2 auto} use the
- * no-staging path for registered buffers (default 2: when the context has at most 10 host threads per GPU);
+ * "slots" N (chunks one host worker keeps in flight, default 3); "raw_inputs" how a flat batch's bases reach the GPU:
+ * 0 = 4-bit staged by host threads (round-1 path), 1 = copied in place from registered buffers (1 byte per base, no host
+ * pass), 3 = packed 2 bit per base by host threads, 2 = auto (default: 1 for registered buffers when the GPU has fewer
+ * than 12 host threads, else 3);
  * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
  * "k2_warps" {1,4} warps per K2 task; "fused_l2" {0,1} level 2 as one fused kernel (default 1);
- * experimental kernels, off by default because they measured slower: "k1_pair", "ring", "k2_sub";
+ * "device_plan" {1,0} sort + tile building on the device / on the host; "k2_narrow" {1,0} register path for narrow K2 rows;
+ * "fpga_strict" {0,1} bsw_fpga_batch refuses tasks outside the FPGA's 8-bit envelope; "ring" {0,1} experimental K1 ring kernel
+ * for long tasks (measured slower than K2, off);
  * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 0:
  *                       the batch calls then leave kernel_ms at 0; bsw_resident_run always times its launches) */
 int  bsw_set_option(bsw_ctx *ctx, const char *key, int64_t value);

@@ -71,20 +71,6 @@ def test_rejects_bad_input(B):
     assert e.value.code == B.BSW_ERANGE
 
 
-@pytest.mark.parametrize("name", ["cfg2_150bp", "cfg3_mixed"])
-def test_pair_packed_lane_function(B, O, name):
-    """K1P (two tasks per lane, int16x2-packed scores; bsw_k1p_core.cuh) must give the same answers as K1 and the oracle."""
-    import ctypes as C
-    flag = C.c_int.in_dll(B.emu_lib(), "bsw_emu_pair")
-    flag.value = 1
-    try:
-        run_both(B, O, B.synth_tasks(name, 6000, seed=8))
-        run_both(B, O, B.synth_tasks(name, 3000, seed=9), o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30)
-        run_both(B, O, B.synth_tasks(name, 3000, seed=10, n_frac=0.02))      # N tasks fall back to K1's matrix path
-    finally:
-        flag.value = 0
-
-
 @pytest.mark.parametrize("w,zdrop,variant", [(100, 100, 1), (10, 100, 1), (5, 0, 1), (100, 100, 2), (7, 50, 2)])
 def test_fused_seed_task_lane_function(B, O, w, zdrop, variant):
     """K3 (bsw_k3_core.cuh): left + right extension, band retry, clip decision per lane == the oracle's chain2aln."""
@@ -135,7 +121,7 @@ def test_ring_overflow_is_reported(B, O):
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_randomised_small_tasks(B, O, seed):
     """Thousands of adversarial little tasks (h0 down to 1, w down to 0, ties, indels) under random scoring, both variants,
-    through K1, K1P and K1R lane functions."""
+    through the K1 and K1R lane functions."""
     from helpers import random_small_tasks
     rng = np.random.default_rng(1000 + seed)
     t = random_small_tasks(rng, 3000)
@@ -144,12 +130,7 @@ def test_randomised_small_tasks(B, O, seed):
     for pk in pks:
         for variant in (1, 2):
             run_both(B, O, t, variant=variant, **pk)
-        flags = _emu_flags(B, pair=0, force_kernel=0, k2_min_qlen=0, ring=0)
-        flags["pair"].value = 1
-        try:
-            run_both(B, O, t, **pk)
-        finally:
-            flags["pair"].value = 0
+        flags = _emu_flags(B, force_kernel=0, k2_min_qlen=0, ring=0)
         flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 0, 8, 1
         try:
             run_both(B, O, t, **pk)

@@ -454,17 +454,6 @@ def test_multi_device_context_shards_without_collective(B, O):
     assert_same(co, cg.astype(np.int64), "multi-device cells")
 
 
-def test_k1p_two_tasks_per_lane(B, O, ctx):
-    """Optional K1P kernel (k1_pair=1): int16x2 lanes carrying two tasks each."""
-    ctx.set_option("k1_pair", 1)
-    try:
-        both(B, O, ctx, B.synth_tasks("cfg2_150bp", 40_000, seed=50))
-        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 40_000, seed=51))
-        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 10_000, seed=52, n_frac=0.01), o_del=4, e_del=2, o_ins=7, e_ins=1)
-    finally:
-        ctx.set_option("k1_pair", 0)
-
-
 def test_level2_host_orchestrated_and_long_flanks(B, O, ctx):
     """fused_l2=0 (four level-1 passes) gives the same records; seeds with a flank beyond a K1 tile take that path anyway."""
     t = B.synth_tasks("cfg3_mixed", 2000, seed=70)
@@ -497,17 +486,15 @@ def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
     both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=82))          # default: K2 (one warp per task, ring row buffer)
     both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=83), opts={"k2_warps": 4})
     ctx.set_option("k2_warps", 1)
-    # K2S (option k2_sub): 8 lanes per task, 512-column ring, overflowing tasks rerun on K2
-    both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=85), opts={"k2_sub": 1})
-    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=86, n_frac=0.02), opts={"k2_sub": 1, "force_kernel": 2})
     rng = np.random.default_rng(6)
     qs, ts = [], []
-    for k in range(12):                                       # near-perfect 3 kb matches: windows outgrow K2S's 512-column ring
+    for k in range(12):                                       # near-perfect 3 kb matches: rows as wide as the band allows
         q = rng.integers(0, 4, 3000).astype(np.uint8)
         qs.append(q); ts.append(np.concatenate([q, q[:200]]).astype(np.uint8))
     qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
-    both(B, O, ctx, dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.full(12, 400, np.int32), w=np.full(12, 400, np.int32)), opts={"k2_sub": 1})
-    ctx.set_option("k2_sub", 0)
+    wide = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.full(12, 400, np.int32), w=np.full(12, 400, np.int32))
+    both(B, O, ctx, wide)
+    both(B, O, ctx, wide, opts={"k2_narrow": 0}); ctx.set_option("k2_narrow", 1)
 
 
 def _k1r_cases(B, O, ctx):
@@ -528,8 +515,8 @@ def _k1r_cases(B, O, ctx):
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
-    """Adversarial little tasks (h0 down to 1, w down to 0, ties, indels), random scoring, through K1, K1P, K1R, K2 (1 and 4
-    warps), K2S and the fused level 2."""
+    """Adversarial little tasks (h0 down to 1, w down to 0, ties, indels), random scoring, through K1, K1R, K2 (1 and 4
+    warps, both variants, with and without the narrow-row path) and the fused level 2."""
     from helpers import random_small_tasks
     rng = np.random.default_rng(2000 + seed)
     t = random_small_tasks(rng, 4000)
@@ -538,11 +525,11 @@ def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
     for p in (dict(), pk):
         both(B, O, ctx, t, **p)
         both(B, O, ctx, t, variant=2, **p)
-        both(B, O, ctx, t, opts={"k1_pair": 1}, **p); ctx.set_option("k1_pair", 0)
         both(B, O, ctx, t, opts={"ring": 1, "k2_min_qlen": 8}, **p); ctx.set_option("ring", 0)
         both(B, O, ctx, t, opts={"force_kernel": 2}, **p)
         both(B, O, ctx, t, opts={"force_kernel": 2, "k2_warps": 4}, **p); ctx.set_option("k2_warps", 1)
-        both(B, O, ctx, t, opts={"force_kernel": 2, "k2_sub": 1}, **p); ctx.set_option("k2_sub", 0)
+        both(B, O, ctx, t, opts={"force_kernel": 2, "k2_narrow": 0}, **p); ctx.set_option("k2_narrow", 1)
+        both(B, O, ctx, t, variant=2, opts={"force_kernel": 2}, **p)
     # level 2 on random flank pairs
     n = 2000
     seeds = []

@@ -64,9 +64,9 @@ if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "sweep")
         fails += parity(ctx, "cfg4_long", 64)
         fails += parity(ctx, "cfg3_mixed", 5000, opts={"force_kernel": 2}, o_del=4, e_del=2, o_ins=7, e_ins=1)
     if what == "long":
-        for opts in ({"k2_sub": 1}, {"k2_sub": 0, "k2_warps": 1}, {"k2_sub": 0, "k2_warps": 4}):
+        for opts in ({"k2_narrow": 0}, {"k2_narrow": 1, "k2_warps": 1}, {"k2_warps": 4}):
             timing(ctx, "cfg4_long", 20000, reps=2, opts=opts)
-        ctx.set_option("k2_sub", 0); ctx.set_option("k2_warps", 1)
+        ctx.set_option("k2_narrow", 1); ctx.set_option("k2_warps", 1)
     if what in ("all", "timing"):
         timing(ctx, "cfg2_150bp", 1000000)
         timing(ctx, "cfg3_mixed", 200000)

@@ -1,4 +1,4 @@
-"""Small run over every kernel path (K0, K1 fast/matrix/V2, K1P, K1R, K2, K2S, K3) for compute-sanitizer."""
+"""Small run over every kernel path (K0, planner, K1 fast/matrix/V2, K1R, K2 V1/V2, K3) for compute-sanitizer."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -24,18 +24,17 @@ def check(name, n, variant=1, n_frac=0.0, **opts):
     print(name, n, variant, n_frac, opts, "OK" if ok else "MISMATCH", flush=True)
     bad += 0 if ok else 1
     for k in opts:
-        ctx.set_option(k, {"force_kernel": 0, "k1_pair": 0, "ring": 0, "k2_sub": 0, "k2_warps": 1, "k2_min_qlen": 384}[k])
+        ctx.set_option(k, {"force_kernel": 0, "ring": 0, "k2_narrow": 1, "k2_warps": 1, "k2_min_qlen": 384}[k])
     ctx.set_option("variant", 1)
 
 
 check("cfg3_mixed", 1500)
 check("cfg3_mixed", 1500, n_frac=0.02)
 check("cfg3_mixed", 1500, variant=2)
-check("cfg3_mixed", 1500, k1_pair=1)
 check("cfg3_mixed", 1500, ring=1, k2_min_qlen=64)
 check("cfg3_mixed", 600, force_kernel=2)
 check("cfg3_mixed", 600, force_kernel=2, k2_warps=4)
-check("cfg3_mixed", 600, force_kernel=2, k2_sub=1)
+check("cfg3_mixed", 600, variant=2, force_kernel=2)
 check("cfg4_long", 6)
 t = B.synth_tasks("cfg3_mixed", 1000, seed=4)
 seeds = seeds_from_flat(t, 500, unset_score_every=3)
