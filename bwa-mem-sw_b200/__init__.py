@@ -61,6 +61,10 @@ class Task(C.Structure):
                 ("h0", C.c_int32), ("w", C.c_int32)]
 
 
+class GlobalTask(C.Structure):
+    _fields_ = [("query", C.c_void_p), ("target", C.c_void_p), ("qlen", C.c_int32), ("tlen", C.c_int32), ("w", C.c_int32)]
+
+
 class SeedTask(C.Structure):
     _fields_ = [("q_left", C.c_void_p), ("q_right", C.c_void_p), ("t_left", C.c_void_p), ("t_right", C.c_void_p),
                 ("qlen", C.c_int32 * 2), ("tlen", C.c_int32 * 2),
@@ -309,6 +313,19 @@ class Context:
         return rbb, nres.value
 
     fpga_batch = pe_array_batch
+
+    # ---- ksw_global2: banded global alignment + CIGAR ----
+    def global_batch(self, params: Params, queries, targets, w, max_ops: int = 256):
+        """queries / targets: lists of uint8 arrays; w: per-task band.  Returns (score int32[n], list of uint32 CIGAR arrays)."""
+        n = len(queries)
+        qs = [_u8(q) for q in queries]; ts = [_u8(t) for t in targets]
+        tasks = (GlobalTask * n)()
+        for i in range(n):
+            tasks[i].query, tasks[i].target = qs[i].ctypes.data, ts[i].ctypes.data
+            tasks[i].qlen, tasks[i].tlen, tasks[i].w = len(qs[i]), len(ts[i]), int(w[i])
+        score = np.zeros(n, dtype=np.int32); ncig = np.zeros(n, dtype=np.int32); cig = np.zeros(n * max_ops, dtype=np.uint32)
+        self._check(lib().bsw_global_batch(self.handle, C.byref(params), tasks, n, max_ops, score.ctypes.data, ncig.ctypes.data, cig.ctypes.data))
+        return score, [cig[i * max_ops: i * max_ops + ncig[i]].copy() for i in range(n)]
 
     # ---- async pair ----
     def submit(self, params: Params, tasks, n, out):

@@ -126,6 +126,24 @@ struct LaunchArgs {
     int32_t          w, pen_clip5, pen_clip3;
 };
 
+// K4 (banded global alignment with traceback, ksw_global2)
+struct GlobalTask { uint32_t qoff, toff; int32_t qlen, tlen, w; };
+struct GlobalArgs {
+    const GlobalTask* tasks;
+    const uint8_t* qbuf;           // concatenated queries / targets, one base code per byte
+    const uint8_t* tbuf;
+    int32_t*  eh;                  // row state workspace: tile t starts at eh_off[t] * 32 ints
+    uint8_t*  z;                   // direction bytes:     tile t starts at z_off[t] * 32 bytes
+    const uint32_t* eh_off;
+    const uint64_t* z_off;
+    int32_t*  score;
+    int32_t*  n_cigar;             // -1: more than max_ops operations
+    uint32_t* cigar;               // [ntasks * max_ops]
+    uint32_t  ntasks;
+    int32_t   max_ops;
+    DevParams p;
+};
+
 constexpr int STATUS_OK = 0;
 constexpr int STATUS_OVERFLOW = 1;  // K1R: the live window outgrew the ring; the host reruns the task on K2
 constexpr int STATUS_HAS_N = 2;     // raw mode: the task holds an N and ran on the +a/-b kernel; the host reruns it with matrix lookup

@@ -1509,6 +1509,108 @@ int bsw_chain2aln_batch(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_task*
     return bsw_chain2aln_impl(ctx, P, tasks, n, nullptr, out);
 }
 
+
+// ---------------- banded global alignment with traceback (ksw_global2) ----------------
+// The DP that follows seed extension in BWA-MEM (bwa_gen_cigar2 -> ksw_global2, once per reported alignment).  A plain
+// driver: chunks bounded by the traceback workspace (one direction byte per cell), one stream, tiles of 32 tasks in
+// input order -- the call is far from the hot path (one alignment per read against tens of extensions).
+int bsw_global_batch(bsw_ctx* ctx, const bsw_params* params, const bsw_global_task* tasks, size_t n, int max_ops,
+                     int32_t* score, int32_t* n_cigar, uint32_t* cigar)
+{
+    if (!ctx) return BSW_EINVAL;
+    if (n == 0) return BSW_OK;
+    if (!params || !tasks || !score || !n_cigar || !cigar || max_ops < 1) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
+    int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; ++i) {
+        const bsw_global_task& t = tasks[i];
+        if (!t.query || !t.target || t.qlen < 1 || t.tlen < 1 || t.w < 0 || t.qlen > 100000 || t.tlen > 100000) {
+            set_error(ctx, "global task " + std::to_string(i) + ": bad length, band or null sequence"); return BSW_EINVAL;
+        }
+        // bwa_gen_cigar2 widens the band to at least the length difference before it calls ksw_global2: a narrower band
+        // cannot reach the last cell and the traceback would leave the stored band
+        if (t.w < std::abs(t.tlen - t.qlen)) { set_error(ctx, "global task " + std::to_string(i) + ": band narrower than |tlen - qlen|"); return BSW_EINVAL; }
+        for (int k = 0; k < t.qlen; ++k) if (t.query[k] > 4) { set_error(ctx, "global task " + std::to_string(i) + ": invalid (base code > 4)"); return BSW_EINVAL; }
+        for (int k = 0; k < t.tlen; ++k) if (t.target[k] > 4) { set_error(ctx, "global task " + std::to_string(i) + ": invalid (base code > 4)"); return BSW_EINVAL; }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].id));
+    cudaStream_t st = nullptr;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t z_budget = (size_t)1 << 30;                         // bytes of direction matrix per chunk
+    std::vector<GlobalTask> gt;
+    std::vector<uint8_t> qb, tb;
+    std::vector<uint32_t> eh_off;
+    std::vector<uint64_t> z_off;
+    size_t first = 0;
+    auto fail = [&](int code) { cudaStreamDestroy(st); cudaSetDevice(prev); return code; };
+    while (first < n) {
+        gt.clear(); qb.clear(); tb.clear(); eh_off.clear(); z_off.clear();
+        uint64_t z_rows = 0; uint64_t eh_rows = 0;
+        size_t count = 0;
+        while (first + count < n && count < 65536) {
+            // one tile of up to 32 tasks
+            const size_t tn = std::min<size_t>(TILE_LANES, n - first - count);
+            uint64_t zmax = 0; int qmax = 0;
+            for (size_t k = 0; k < tn; ++k) {
+                const bsw_global_task& t = tasks[first + count + k];
+                const uint64_t ncol = (uint64_t)std::min(t.qlen, 2 * t.w + 1);
+                zmax = std::max<uint64_t>(zmax, ncol * (uint64_t)t.tlen);
+                qmax = std::max(qmax, t.qlen);
+            }
+            if (count > 0 && (z_rows + zmax) * TILE_LANES > z_budget) break;
+            if (zmax * TILE_LANES > ((size_t)8 << 30)) { set_error(ctx, "global task " + std::to_string(first + count) + ": traceback matrix too large"); return fail(BSW_ERANGE); }
+            eh_off.push_back((uint32_t)eh_rows); z_off.push_back(z_rows);
+            eh_rows += 2 * (uint64_t)(qmax + 2); z_rows += zmax;
+            for (size_t k = 0; k < tn; ++k) {
+                const bsw_global_task& t = tasks[first + count + k];
+                gt.push_back(GlobalTask{ (uint32_t)qb.size(), (uint32_t)tb.size(), t.qlen, t.tlen, t.w });
+                qb.insert(qb.end(), t.query, t.query + t.qlen); tb.insert(tb.end(), t.target, t.target + t.tlen);
+            }
+            count += tn;
+        }
+        GlobalArgs a{};
+        void *d_tasks = nullptr, *d_q = nullptr, *d_t = nullptr, *d_eh = nullptr, *d_z = nullptr, *d_eo = nullptr, *d_zo = nullptr, *d_sc = nullptr, *d_nc = nullptr, *d_cg = nullptr;
+        auto release = [&]() { for (void* p : { d_tasks, d_q, d_t, d_eh, d_z, d_eo, d_zo, d_sc, d_nc, d_cg }) if (p) cudaFree(p); };
+#define G_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { release(); int c__ = cuda_fail(ctx, e__, #call); return fail(c__); } } while (0)
+        G_TRY(cudaMalloc(&d_tasks, gt.size() * sizeof(GlobalTask)));
+        G_TRY(cudaMalloc(&d_q, qb.size() + 16)); G_TRY(cudaMalloc(&d_t, tb.size() + 16));
+        G_TRY(cudaMalloc(&d_eh, (size_t)eh_rows * TILE_LANES * sizeof(int32_t)));
+        G_TRY(cudaMalloc(&d_z, (size_t)z_rows * TILE_LANES + 16));
+        G_TRY(cudaMalloc(&d_eo, eh_off.size() * sizeof(uint32_t))); G_TRY(cudaMalloc(&d_zo, z_off.size() * sizeof(uint64_t)));
+        G_TRY(cudaMalloc(&d_sc, count * sizeof(int32_t))); G_TRY(cudaMalloc(&d_nc, count * sizeof(int32_t)));
+        G_TRY(cudaMalloc(&d_cg, count * (size_t)max_ops * sizeof(uint32_t)));
+        G_TRY(cudaMemcpyAsync(d_tasks, gt.data(), gt.size() * sizeof(GlobalTask), cudaMemcpyHostToDevice, st));
+        G_TRY(cudaMemcpyAsync(d_q, qb.data(), qb.size(), cudaMemcpyHostToDevice, st));
+        G_TRY(cudaMemcpyAsync(d_t, tb.data(), tb.size(), cudaMemcpyHostToDevice, st));
+        G_TRY(cudaMemcpyAsync(d_eo, eh_off.data(), eh_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        G_TRY(cudaMemcpyAsync(d_zo, z_off.data(), z_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        a.tasks = static_cast<const GlobalTask*>(d_tasks); a.qbuf = static_cast<const uint8_t*>(d_q); a.tbuf = static_cast<const uint8_t*>(d_t);
+        a.eh = static_cast<int32_t*>(d_eh); a.z = static_cast<uint8_t*>(d_z); a.eh_off = static_cast<const uint32_t*>(d_eo); a.z_off = static_cast<const uint64_t*>(d_zo);
+        a.score = static_cast<int32_t*>(d_sc); a.n_cigar = static_cast<int32_t*>(d_nc); a.cigar = static_cast<uint32_t*>(d_cg);
+        a.ntasks = (uint32_t)count; a.max_ops = max_ops; a.p = dp;
+        G_TRY(k4_launch(a, st));
+        G_TRY(cudaMemcpyAsync(score + first, d_sc, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        G_TRY(cudaMemcpyAsync(n_cigar + first, d_nc, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        G_TRY(cudaMemcpyAsync(cigar + first * (size_t)max_ops, d_cg, count * (size_t)max_ops * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        G_TRY(cudaStreamSynchronize(st));
+#undef G_TRY
+        release();
+        {
+            std::lock_guard<std::mutex> g(ctx->err_mu);
+            ctx->stats.kernel_launches += 1; ctx->stats.tasks += count;
+        }
+        first += count;
+    }
+    cudaStreamDestroy(st);
+    cudaSetDevice(prev);
+    for (size_t i = 0; i < n; ++i)
+        if (n_cigar[i] < 0) { set_error(ctx, "global task " + std::to_string(i) + ": the alignment needs more than max_ops CIGAR operations"); return BSW_ERANGE; }
+    return BSW_OK;
+}
+
 void bsw_set_error_text(bsw_ctx* ctx, const char* text) { set_error(ctx, text ? text : ""); }
 int bsw_option_value(bsw_ctx* ctx, const char* key)
 {

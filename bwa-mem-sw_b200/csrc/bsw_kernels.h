@@ -52,6 +52,9 @@ cudaError_t k2_launch(const LaunchArgs& a, int generic, int warps, int variant, 
 size_t k2_smem_bytes(int qmax, int wmax);
 
 
+// K4: banded global alignment with traceback (ksw_global2), one lane per task.
+cudaError_t k4_launch(const GlobalArgs& a, cudaStream_t st);
+
 // INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
 // streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.
 cudaError_t int_peak_run(double out_ops[5], double* sm_clock_mhz, int* sm_count, cudaStream_t st);

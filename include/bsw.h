@@ -148,6 +148,15 @@ int bsw_build_seed_tasks(const bsw_chain_opt *opt, const uint8_t *query, int l_q
 /* Record (relative to the seed, as the PE returns it) -> absolute coordinates, with BWA's rule for a seed without flanks. */
 void bsw_finish_seed(const bsw_chain_opt *opt, const bsw_chain_seed *seed, int l_query, const bsw_aln_record *rec, bsw_seed_aln *out);
 
+/* ---------------- after the extension: banded global alignment with traceback (ksw_global2) ---------------- */
+/* the DP BWA-MEM runs once per reported alignment (bwa_gen_cigar2 -> ksw_global2) to turn the extension's
+ * end points into a CIGAR.  Not part of the reference tree (the FPGA stops at the extension); follows the published BWA
+ * algorithm.  Scores are int32.  cigar[i*max_ops .. +n_cigar[i]) = task i's operations in BAM encoding (len << 4 | op;
+ * op 0 = M, 1 = I, 2 = D).  BSW_ERANGE if an alignment needs more than max_ops operations. */
+typedef struct { const uint8_t *query, *target; int32_t qlen, tlen, w; } bsw_global_task;
+int bsw_global_batch(bsw_ctx *ctx, const bsw_params *params, const bsw_global_task *tasks, size_t n, int max_ops,
+                     int32_t *score, int32_t *n_cigar, uint32_t *cigar);
+
 /* ---------------- level 3: FPGA wire format ---------------- */
 #define BSW_TBB_WORDS 65536   /* 4096 x 64 B (bwa_mem_sw.v:163-166) */
 #define BSW_RBB_WORDS 4096    /*  256 x 64 B (bwa_mem_sw.v:167-170) */

@@ -80,6 +80,8 @@ def lib():
                                               C.POINTER(C.c_int64)]
         _lib.bswref_sw_extend_rtl8.restype = None
         _lib.bswref_sw_extend_rtl8.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
+        _lib.bswref_global.restype = C.c_int
+        _lib.bswref_global.argtypes = [C.POINTER(Params), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         _lib.bswref_max_threads.restype = C.c_int
         _lib.bswref_clamp_w.restype = C.c_int
         _lib.bswref_clamp_w.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int]
@@ -197,3 +199,15 @@ def chain2aln_rtl(params2: Params2, seed_tasks, gaps):
         lib().bswref_chain2aln_rtl(C.byref(params2), C.byref(seed_tasks[i]), gaps[i].ctypes.data,
                                    out[i:i + 1].ctypes.data, C.byref(cells))
     return out, int(cells.value)
+
+
+def global_align(params: Params, query, target, w: int, max_cigar: int = 512):
+    """ksw_global2 restated (banded global alignment + traceback; SURVEY 8 f.4, parity unpinned -- see the C file).
+    Returns (score, cigar uint32[n] in BAM encoding len << 4 | op with 0 = M, 1 = I, 2 = D), or (score, None) when the
+    alignment needs more than max_cigar operations."""
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    cig = np.zeros(max_cigar, dtype=np.uint32)
+    n = C.c_int(0)
+    score = lib().bswref_global(C.byref(params), len(q), q.ctypes.data, len(t), t.ctypes.data, int(w), max_cigar, cig.ctypes.data, C.byref(n))
+    return int(score), (cig[:n.value].copy() if n.value >= 0 else None)

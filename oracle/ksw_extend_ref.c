@@ -396,3 +396,82 @@ void bswref_chain2aln_batch(const bswref_params2 *P, int variant, int64_t n,
     bswref_parallel_for(n, 64, nthreads, l2_range, &a);
     if (cells_total) *cells_total = (int64_t)atomic_load(&a.cells);
 }
+
+/* =====================================================================================================================
+ * ksw_global2 -- banded global alignment with affine gaps and traceback, the DP that follows the extension in BWA-MEM
+ * (bwa_gen_cigar2 calls it once per reported alignment).  NOT part of /root/reference and not
+ * derivable from the RTL: this restates the published BWA algorithm (ksw.c, 0.7.x) from its description -- query in the
+ * inner loop, eh[j] = {H(i-1,j-1), E(i,j)}, M separated from H so that the direction is recorded correctly, one byte
+ * per cell holding the H direction (bits 0-1) and the "E / F extends" flags for the next cell (bit 2, bit 5).
+ * PARITY UNPINNED for this function: no source, no vectors, no RTL -- it is the oracle of SURVEY row f.4 only.
+ * cigar: BAM encoding (len << 4 | op), op 0 = M, 1 = I, 2 = D; returns the score, *n_cigar = number of operations
+ * (or -1 if more than max_cigar would be needed).
+ * ===================================================================================================================== */
+#define BSWREF_MINUS_INF (-0x40000000)
+
+static int push_op(uint32_t *cigar, int n, int max_cigar, int op, int len)
+{
+    if (n > 0 && (cigar[n - 1] & 0xf) == (uint32_t)op) { cigar[n - 1] += (uint32_t)len << 4; return n; }
+    if (n >= max_cigar) return -1;
+    cigar[n] = (uint32_t)len << 4 | (uint32_t)op;
+    return n + 1;
+}
+
+int bswref_global(const bswref_params *p, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int w,
+                  int max_cigar, uint32_t *cigar, int *n_cigar)
+{
+    const int o_del = p->o_del, e_del = p->e_del, o_ins = p->o_ins, e_ins = p->e_ins;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    int32_t *eh_h = (int32_t *)malloc(sizeof(int32_t) * (size_t)(qlen + 1));
+    int32_t *eh_e = (int32_t *)malloc(sizeof(int32_t) * (size_t)(qlen + 1));
+    uint8_t *z = (uint8_t *)malloc((size_t)n_col * (size_t)tlen + 1);
+    int i, j, k, score, n = 0, which = 0;
+    eh_h[0] = 0; eh_e[0] = BSWREF_MINUS_INF;
+    for (j = 1; j <= qlen && j <= w; ++j) { eh_h[j] = -(o_ins + e_ins * j); eh_e[j] = BSWREF_MINUS_INF; }
+    for (; j <= qlen; ++j) eh_h[j] = eh_e[j] = BSWREF_MINUS_INF;                  /* everything outside the band */
+    for (i = 0; i < tlen; ++i) {
+        int32_t f = BSWREF_MINUS_INF, h1;
+        const int8_t *srow = &p->mat[5 * target[i]];
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        uint8_t *zi = &z[(size_t)i * (size_t)n_col];
+        h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : BSWREF_MINUS_INF;
+        for (j = beg; j < end; ++j) {
+            int32_t h, m = eh_h[j], e = eh_e[j], t;
+            uint8_t d;
+            eh_h[j] = h1;
+            m += srow[query[j]];
+            d = m >= e ? 0 : 1;
+            h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            h1 = h;
+            t = m - oe_del;
+            e -= e_del;
+            d |= e > t ? 1 << 2 : 0;
+            e = e > t ? e : t;
+            eh_e[j] = e;
+            t = m - oe_ins;
+            f -= e_ins;
+            d |= f > t ? 2 << 4 : 0;
+            f = f > t ? f : t;
+            zi[j - beg] = d;
+        }
+        eh_h[end] = h1; eh_e[end] = BSWREF_MINUS_INF;
+    }
+    score = eh_h[qlen];
+    i = tlen - 1; k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;                  /* (i,k): the last cell */
+    while (i >= 0 && k >= 0 && n >= 0) {
+        which = z[(size_t)i * (size_t)n_col + (size_t)(k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+        if (which == 0) { n = push_op(cigar, n, max_cigar, 0, 1); --i; --k; }
+        else if (which == 1) { n = push_op(cigar, n, max_cigar, 2, 1); --i; }
+        else { n = push_op(cigar, n, max_cigar, 1, 1); --k; }
+    }
+    if (n >= 0 && i >= 0) n = push_op(cigar, n, max_cigar, 2, i + 1);
+    if (n >= 0 && k >= 0) n = push_op(cigar, n, max_cigar, 1, k + 1);
+    for (i = 0; n > 0 && i < n >> 1; ++i) { const uint32_t tmp = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = tmp; }
+    *n_cigar = n;
+    free(eh_h); free(eh_e); free(z);
+    return score;
+}
