@@ -63,7 +63,8 @@ def native_oracle():
         os.makedirs(out_dir, exist_ok=True)
         so = os.path.join(out_dir, "libbswref.so")
         subprocess.check_call(["gcc", "-O3", "-march=native", "-pthread", "-fPIC", "-std=c11", "-shared", "-o", so,
-                               os.path.join(ROOT, "oracle", "ksw_extend_ref.c")], stderr=subprocess.DEVNULL)
+                               os.path.join(ROOT, "oracle", "ksw_extend_ref.c"), os.path.join(ROOT, "oracle", "rtl_width_model.c")],
+                              stderr=subprocess.DEVNULL)
         O.use_library(so)
         return "gcc -O3 -march=native"
     except Exception:

@@ -151,7 +151,9 @@ def lib() -> C.CDLL:
         L.bsw_extend_batch.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp]
         L.bsw_extend_batch_flat.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp]
         L.bsw_chain2aln_batch.argtypes = [vp, C.POINTER(Params2), vp, C.c_size_t, vp]
+        L.bsw_global_batch.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, i32, vp, vp, vp]
         L.bsw_fpga_batch.argtypes = [vp, vp, vp, C.POINTER(i32)]
+        L.bsw_fpga_envelope.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.bsw_tbb_encode.argtypes = [C.POINTER(Params2), vp, C.c_size_t, vp]
         L.bsw_rbb_decode.argtypes = [vp, C.c_size_t, vp]
         L.bsw_submit.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.POINTER(Ticket)]

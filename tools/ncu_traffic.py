@@ -2,9 +2,9 @@
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file gpurun_out/r02_dram_bytes.csv python tools/k1_prof.py cfg2_150bp 1000000
-    python tools/ncu_traffic.py gpurun_out/r02_dram_bytes.csv 3
+    python tools/ncu_traffic.py gpurun_out/r02_dram_bytes.csv 4
 
-tools/k1_prof.py runs the resident pass three times (two warm, one reported); the bytes are summed per kernel family over
+tools/k1_prof.py runs the resident pass four times (one inside bsw_resident_create, two warm, one reported); the bytes are summed per kernel family over
 all launches and divided by the number of passes (second argument).  bench.py reads the file for `roofline.traffic`."""
 import csv, json, os, subprocess, sys
 
