@@ -144,6 +144,18 @@ struct GlobalArgs {
     DevParams p;
 };
 
+// K5 (wide extension: 32-bit row state in global memory, one warp per task)
+struct WideTask { uint64_t row_off; uint32_t qoff, toff; int32_t qlen, tlen, h0, w; };   // row_off: int32 units into `rows`; 2 * (qlen + 2) of them
+struct WideArgs {
+    const WideTask* tasks;
+    const uint8_t* qbuf;           // concatenated queries / targets, one base code per byte
+    const uint8_t* tbuf;
+    int32_t* rows;
+    SlotResult* out;               // [ntasks]
+    uint32_t ntasks;
+    DevParams p;
+};
+
 constexpr int STATUS_OK = 0;
 constexpr int STATUS_OVERFLOW = 1;  // K1R: the live window outgrew the ring; the host reruns the task on K2
 constexpr int STATUS_HAS_N = 2;     // raw mode: the task holds an N and ran on the +a/-b kernel; the host reruns it with matrix lookup

@@ -143,6 +143,8 @@ struct bsw_ctx {
                                    // 0 never, 1 always, 2 auto (when there are at most 10 host threads per GPU)
     std::vector<std::pair<const unsigned char*, size_t>> host_regs;   // registered host ranges      // chunks one worker keeps in flight
     int k2_warps = 1;              // warps per K2 task (1: most tasks per SM; 4: widest rows in parallel)
+    int wide = 1;                  // tasks outside the 16-bit envelope of K1 / K2: 0 = refuse the batch (BSW_ERANGE), 1 = run them on K5
+                                   // (32-bit rows), 2 = run EVERY task on K5 (tests)
     bool fpga_strict = false;      // bsw_fpga_batch refuses (BSW_ERANGE) batches with a task outside the FPGA's 8-bit envelope
     bool k2_narrow = true;         // K2 rows below 64 columns run in registers (bsw_k2.cu::k2_narrow_row)
     bool device_plan = true;       // the chunk's sort + tile building run on the device (bsw_plan.cu); false: host build_plan
@@ -960,17 +962,103 @@ void fill_subset(const void* self, size_t first, size_t count, ExtTask* out)
     for (size_t k = 0; k < count; ++k) S.base->fill(S.base->self, S.idx[first + k], 1, out + k);
 }
 
-int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+// 0: the 16-bit kernels take the task; 1: only K5 can; BSW_EINVAL / BSW_ERANGE: nobody can
+int wide_class(const ExtTask& t, int max_mat, const DevParams& dp)
 {
-    if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
-    if (n == 0) return BSW_OK;
-    CallLease lease(ctx);
-    bsw_ctx::CallState& cs = *lease.cs;
+    if (!t.q || !t.t || t.qlen < 1 || t.tlen < 1 || t.h0 < 1 || t.w < 0) return BSW_EINVAL;
+    if ((int64_t)t.h0 + (int64_t)t.qlen * max_mat <= SCORE_CAP && t.qlen <= K2_QLEN_CAP && t.tlen <= 500000) return 0;
+    const int64_t e = std::max(dp.e_del, dp.e_ins);
+    if (t.qlen > WIDE_QLEN_CAP || t.tlen > WIDE_TLEN_CAP || (int64_t)t.h0 + (int64_t)t.qlen * ((int64_t)max_mat + dp.e_ins) > WIDE_SCORE_CAP ||
+        (int64_t)std::max(t.qlen, t.tlen) * e > WIDE_SCORE_CAP) return BSW_ERANGE;
+    return 1;
+}
+
+// The tasks idx[0..m) (or tasks 0..m when idx is null) on K5: chunks bounded by bases and row workspace, one stream on
+// the context's first device.  A correctness path for rare tasks, not a pipeline.
+int run_wide(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, const size_t* idx, size_t m, bsw_result* out, uint32_t* cells)
+{
+    DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
+    int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
+    if (rc) return rc;
+    int prev = 0, sms = 148;
+    cudaGetDevice(&prev);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->devs[0].id));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->devs[0].id);
+    cudaStream_t st = nullptr;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    auto fail = [&](int code) { cudaStreamDestroy(st); cudaSetDevice(prev); return code; };
+    std::vector<WideTask> wt;
+    std::vector<uint8_t> qb, tb;
+    std::vector<SlotResult> res;
+    size_t first = 0;
+    uint64_t launches = 0, ntask = 0, ncells = 0;
+    while (first < m) {
+        wt.clear(); qb.clear(); tb.clear();
+        uint64_t rows = 0;
+        size_t count = 0;
+        while (first + count < m && count < 65536 && qb.size() + tb.size() < ((size_t)256 << 20) && rows < ((uint64_t)64 << 20)) {
+            const size_t task = idx ? idx[first + count] : first + count;
+            ExtTask t;
+            src.fill(src.self, task, 1, &t);
+            const int c = wide_class(t, max_mat, dp);
+            if (c < 0) {
+                set_error(ctx, "task " + std::to_string(task) + ": qlen=" + std::to_string(t.qlen) + " tlen=" + std::to_string(t.tlen) + " h0=" + std::to_string(t.h0) +
+                               " w=" + std::to_string(t.w) + (c == BSW_ERANGE ? " outside the numeric envelope (32-bit row state / length caps)"
+                                                                             : " invalid (null pointer, length < 1, h0 < 1 or negative band)"));
+                return fail(c);
+            }
+            for (int k = 0; k < t.qlen; ++k) if (t.q[k] > 4) { set_error(ctx, "task " + std::to_string(task) + ": invalid (base code > 4)"); return fail(BSW_EINVAL); }
+            for (int k = 0; k < t.tlen; ++k) if (t.t[k] > 4) { set_error(ctx, "task " + std::to_string(task) + ": invalid (base code > 4)"); return fail(BSW_EINVAL); }
+            wt.push_back(WideTask{ rows, (uint32_t)qb.size(), (uint32_t)tb.size(), t.qlen, t.tlen, t.h0, t.w });
+            rows += 2 * ((uint64_t)t.qlen + 2);
+            qb.insert(qb.end(), t.q, t.q + t.qlen); tb.insert(tb.end(), t.t, t.t + t.tlen);
+            ++count;
+        }
+        void *d_tasks = nullptr, *d_q = nullptr, *d_t = nullptr, *d_rows = nullptr, *d_out = nullptr;
+        auto release = [&]() { for (void* p : { d_tasks, d_q, d_t, d_rows, d_out }) if (p) cudaFree(p); };
+#define W_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { release(); int c__ = cuda_fail(ctx, e__, #call); return fail(c__); } } while (0)
+        W_TRY(cudaMalloc(&d_tasks, count * sizeof(WideTask)));
+        W_TRY(cudaMalloc(&d_q, qb.size() + 16)); W_TRY(cudaMalloc(&d_t, tb.size() + 16));
+        W_TRY(cudaMalloc(&d_rows, (size_t)rows * sizeof(int32_t)));
+        W_TRY(cudaMalloc(&d_out, count * sizeof(SlotResult)));
+        W_TRY(cudaMemcpyAsync(d_tasks, wt.data(), count * sizeof(WideTask), cudaMemcpyHostToDevice, st));
+        W_TRY(cudaMemcpyAsync(d_q, qb.data(), qb.size(), cudaMemcpyHostToDevice, st));
+        W_TRY(cudaMemcpyAsync(d_t, tb.data(), tb.size(), cudaMemcpyHostToDevice, st));
+        WideArgs a{};
+        a.tasks = static_cast<const WideTask*>(d_tasks); a.qbuf = static_cast<const uint8_t*>(d_q); a.tbuf = static_cast<const uint8_t*>(d_t);
+        a.rows = static_cast<int32_t*>(d_rows); a.out = static_cast<SlotResult*>(d_out); a.ntasks = (uint32_t)count; a.p = dp;
+        W_TRY(k5_launch(a, ctx->opt.variant, sms, st));
+        res.resize(count);
+        W_TRY(cudaMemcpyAsync(res.data(), d_out, count * sizeof(SlotResult), cudaMemcpyDeviceToHost, st));
+        W_TRY(cudaStreamSynchronize(st));
+#undef W_TRY
+        release();
+        for (size_t k = 0; k < count; ++k) {
+            const size_t task = idx ? idx[first + k] : first + k;
+            const SlotResult& r = res[k];
+            bsw_result& o = out[task];
+            o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
+            if (cells) cells[task] = (uint32_t)r.cells;
+            ncells += (uint32_t)r.cells;
+        }
+        ++launches; ntask += count;
+        first += count;
+    }
+    cudaStreamDestroy(st);
+    cudaSetDevice(prev);
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    ctx->stats.kernel_launches += launches; ctx->stats.tasks += ntask; ctx->stats.cells_band += ncells;
+    return BSW_OK;
+}
+
+// One pass over a source plus its reruns: K1R tasks whose live window outgrew the ring are rerun on K2, raw-mode tasks
+// that hold an N on the staged path (which classifies them for the matrix-lookup kernel): whole tasks, from scratch,
+// results scattered over the first pass
+int run_with_reruns(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+{
     std::vector<size_t> overflow, rerun_n;
     int rc = run_extensions_locked(ctx, cs, params, src, n, out, cells, -1, &overflow, &rerun_n);
     if (rc) return rc;
-    // K1R tasks whose live window outgrew the ring are rerun on K2, raw-mode tasks that hold an N on the staged path (which
-    // classifies them for the matrix-lookup kernel): whole tasks, from scratch, results scattered over the first pass
     for (int pass = 0; pass < 2; ++pass) {
         std::vector<size_t>& list = pass ? rerun_n : overflow;
         if (list.empty()) continue;
@@ -984,6 +1072,43 @@ int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src
         for (size_t k = 0; k < list.size(); ++k) { out[list[k]] = r2[k]; if (cells) cells[list[k]] = c2[k]; }
     }
     return BSW_OK;
+}
+
+int run_extensions(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
+{
+    if (!ctx || !out) { set_error(ctx, "null argument"); return BSW_EINVAL; }
+    if (n == 0) return BSW_OK;
+    if (ctx->wide == 2) return run_wide(ctx, params, src, nullptr, n, out, cells);
+    CallLease lease(ctx);
+    bsw_ctx::CallState& cs = *lease.cs;
+    int rc = run_with_reruns(ctx, cs, params, src, n, out, cells);
+    if (rc != BSW_ERANGE || ctx->wide == 0) return rc;
+    // Some task is outside the 16-bit envelope (the batch was refused as a whole; rare).  Split it: the tasks K1 / K2 can
+    // take run again as a subset, the others on K5.  A task nobody can take fails the call here with its own message.
+    DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
+    if ((rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat))) return rc;
+    std::vector<size_t> narrow, wide;
+    {
+        std::vector<ExtTask> buf(4096);
+        for (size_t first = 0; first < n; first += buf.size()) {
+            const size_t count = std::min(buf.size(), n - first);
+            src.fill(src.self, first, count, buf.data());
+            for (size_t k = 0; k < count; ++k) {
+                const int c = wide_class(buf[k], max_mat, dp);
+                if (c == 1) wide.push_back(first + k); else narrow.push_back(first + k);      // errors resurface in the narrow pass
+            }
+        }
+    }
+    if (wide.empty()) return BSW_ERANGE;               // refused for another reason: the first pass's message stands
+    if (!narrow.empty()) {
+        const SubsetSrc sub{ &src, narrow.data() };
+        std::vector<bsw_result> r2(narrow.size());
+        std::vector<uint32_t> c2(cells ? narrow.size() : 0);
+        rc = run_with_reruns(ctx, cs, params, TaskSource{ &sub, fill_subset }, narrow.size(), r2.data(), cells ? c2.data() : nullptr);
+        if (rc) return rc;
+        for (size_t k = 0; k < narrow.size(); ++k) { out[narrow[k]] = r2[k]; if (cells) cells[narrow[k]] = c2[k]; }
+    }
+    return run_wide(ctx, params, src, wide.data(), wide.size(), out, cells);
 }
 
 // ---- task sources ----
@@ -1138,6 +1263,7 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "device_plan") { ctx->device_plan = value != 0; }
     else if (k == "k2_narrow") { ctx->k2_narrow = value != 0; }
     else if (k == "fpga_strict") { ctx->fpga_strict = value != 0; }
+    else if (k == "wide") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->wide = (int)value; }
     else if (k == "kernel_timing") { ctx->kernel_timing = value != 0; }
     else if (k == "k2_min_qlen") { if (value < 1) return BSW_EINVAL; ctx->opt.k2_min_qlen = (int)value; }
     else { set_error(ctx, "unknown option " + k); return BSW_EINVAL; }

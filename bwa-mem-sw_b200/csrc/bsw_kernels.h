@@ -55,6 +55,9 @@ size_t k2_smem_bytes(int qmax, int wmax);
 // K4: banded global alignment with traceback (ksw_global2), one lane per task.
 cudaError_t k4_launch(const GlobalArgs& a, cudaStream_t st);
 
+// K5: extension with 32-bit row state in global memory, one warp per task (tasks outside the 16-bit envelope of K1 / K2).
+cudaError_t k5_launch(const WideArgs& a, int variant, int sm_count, cudaStream_t st);
+
 // INT-pipe micro-benchmark (roofline denominator): runs `iters` rounds of dependent-free instruction
 // streams on every SM; out_ops[5] = {add, max, fused add-max (x2 ops), DP-cell mix, add on both pipes} in ops per second.
 cudaError_t int_peak_run(double out_ops[5], double* sm_clock_mhz, int* sm_count, cudaStream_t st);

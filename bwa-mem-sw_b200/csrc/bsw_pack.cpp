@@ -163,7 +163,7 @@ int PACK_TASKS_NAME(const ExtTask* tasks, size_t n, int max_mat, const SchedOpti
             if (msg)
                 *msg = "task " + std::to_string(i) + ": qlen=" + std::to_string(t.qlen) + " tlen=" + std::to_string(t.tlen) +
                        " h0=" + std::to_string(t.h0) + " w=" + std::to_string(t.w) +
-                       (e == BSW_ERANGE ? " outside the numeric envelope (16-bit row state / length caps / V2 long task)"
+                       (e == BSW_ERANGE ? " outside the 16-bit envelope (h0 + qlen * max(mat) <= 32767, qlen <= 40000, tlen <= 500000)"
                                         : " invalid (null pointer, length < 1, h0 < 1 or base code > 4)");
             return e;
         }

@@ -38,6 +38,9 @@ struct SchedOptions {
 constexpr int K1_QLEN_CAP = 1536;        // shared-memory limit of one K1 tile (227 KB / (32 lanes * 4.5 B per column))
 constexpr int K2_QLEN_CAP = 40000;       // shared-memory limit of one K2 task
 constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat) must not exceed this
+// K5 (32-bit rows) takes what K1 / K2 refuse, up to: qlen <= 2^20, tlen <= 2^22, h0 + qlen * (max(mat) + e_ins) and
+// max(qlen, tlen) * max(e_del, e_ins) below 2^30 (so that no intermediate of the recurrence leaves int32)
+constexpr int WIDE_QLEN_CAP = 1 << 20, WIDE_TLEN_CAP = 1 << 22, WIDE_SCORE_CAP = 0x3fffffff;
 
 struct Launch {
     int kind;          // 1 = K1, 2 = K2, 4 = K1R (long tasks, ring row buffer), 5 = K3 (pairs: left tile, right tile)

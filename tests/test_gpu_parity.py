@@ -22,7 +22,7 @@ def both(B, O, ctx, t, variant=1, opts=None, **pk):
         ro, co = O.extend_batch(po, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"], variant=variant)
         rg, cg = ctx.sw_extend_batch(p, t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
     finally:
-        ctx.set_option("variant", 1); ctx.set_option("force_kernel", 0); ctx.set_option("k2_min_qlen", 384)
+        ctx.set_option("variant", 1); ctx.set_option("force_kernel", 0); ctx.set_option("k2_min_qlen", 384); ctx.set_option("wide", 1)
     assert_same(ro, rg, "results")
     assert_same(co.astype(np.int64), cg.astype(np.int64), "cells")
     return ro, co
@@ -135,8 +135,15 @@ def test_empty_batch_and_errors(B, ctx):
     with pytest.raises(B.BswError) as e:                     # h0 must be > 0 (sw_extend precondition)
         ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [0], [100])
     assert e.value.code == B.BSW_EINVAL
-    with pytest.raises(B.BswError) as e:                     # 16-bit row-state envelope
-        ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [40000], [100])
+    ctx.set_option("wide", 0)
+    try:
+        with pytest.raises(B.BswError) as e:                 # 16-bit row-state envelope, with the 32-bit kernel switched off
+            ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [40000], [100])
+        assert e.value.code == B.BSW_ERANGE
+    finally:
+        ctx.set_option("wide", 1)
+    with pytest.raises(B.BswError) as e:                     # beyond the 32-bit kernel's envelope as well
+        ctx.sw_extend_batch(p, qbuf, qoff, tbuf, toff, [0x7fffff00], [100])
     assert e.value.code == B.BSW_ERANGE
     bad = B.make_params(e_del=0)
     with pytest.raises(B.BswError):
@@ -585,7 +592,54 @@ def test_scores_at_the_16_bit_cap(B, O, ctx, variant):
     t["h0"] = np.array([32767 - 2 * len(q) for q in qs], np.int32)
     ro, _ = both(B, O, ctx, t, variant=variant, a=2, b=3, zdrop=0)
     assert int(ro["score"].max()) == 32767
-    t["h0"][5] += 1                                                                                   # one past the cap: rejected, not wrapped
-    with pytest.raises(B.BswError) as e:
-        ctx.sw_extend_batch(B.make_params(a=2, b=3, zdrop=0), t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
-    assert e.value.code == B.BSW_ERANGE
+    t["h0"][5] += 1                                                                                   # one past the cap: never wrapped --
+    ctx.set_option("wide", 0)                                                                         # refused without the 32-bit kernel,
+    try:
+        with pytest.raises(B.BswError) as e:
+            ctx.sw_extend_batch(B.make_params(a=2, b=3, zdrop=0), t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])
+        assert e.value.code == B.BSW_ERANGE
+    finally:
+        ctx.set_option("wide", 1)
+    ro, _ = both(B, O, ctx, t, variant=variant, a=2, b=3, zdrop=0)                                    # exact with it (that one task runs on K5)
+    assert int(ro["score"].max()) == 32768
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_every_task_on_the_32_bit_kernel(B, O, ctx, variant):
+    """Option wide=2 sends every task to K5 (32-bit rows in global memory, one warp per task): the usual corpora must
+    come back bit-exact, cells included -- short reads, N bases, other scorings, z-drop on and off, long reads."""
+    from helpers import random_small_tasks
+    try:
+        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 8_000, seed=31, n_frac=0.01), variant=variant, opts={"wide": 2})
+        both(B, O, ctx, B.synth_tasks("cfg2_150bp", 8_000, seed=32), variant=variant, opts={"wide": 2}, zdrop=0)
+        both(B, O, ctx, random_small_tasks(np.random.default_rng(33), 6000), variant=variant, opts={"wide": 2})
+        both(B, O, ctx, B.synth_tasks("cfg3_mixed", 4_000, seed=34), variant=variant, opts={"wide": 2}, a=2, b=3, o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=20)
+        both(B, O, ctx, B.synth_tasks("cfg4_long", 200, seed=35), variant=variant, opts={"wide": 2})
+    finally:
+        ctx.set_option("wide", 1)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_tasks_beyond_16_bits_in_a_mixed_batch(B, O, ctx, variant):
+    """A batch of ordinary tasks with a few that only 32-bit rows can hold: h0 far above 32767 (scores above 16 bits,
+    with and without mismatches and gaps) and a 45 kb query (longer than K2's shared-memory row).  The call splits the
+    batch -- K1 / K2 for the ordinary tasks, K5 for the rest -- and every task equals the oracle."""
+    rng = np.random.default_rng(91)
+    t = B.synth_tasks("cfg3_mixed", 3000, seed=36)
+    qs = [t["qbuf"][t["qoff"][i]:t["qoff"][i + 1]] for i in range(3000)]
+    ts = [t["tbuf"][t["toff"][i]:t["toff"][i + 1]] for i in range(3000)]
+    h0 = list(t["h0"]); w = list(t["w"])
+    for k, ql in enumerate((200, 3000, 45_000, 700, 12_000)):
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        tt = q.copy()
+        tt[rng.integers(0, ql, max(1, ql // 50))] = rng.integers(0, 4)              # 2 % substitutions
+        cut = int(rng.integers(ql // 3, ql // 2))
+        tt = np.concatenate([tt[:cut], rng.integers(0, 4, 7).astype(np.uint8), tt[cut:], rng.integers(0, 4, 40).astype(np.uint8)])
+        pos = 17 * k + 5
+        qs.insert(pos, q); ts.insert(pos, tt)
+        h0.insert(pos, [70_000, 33_000, 19, 1_000_000, 40_000][k]); w.insert(pos, [100, 150, 200, 50, 300][k])
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    tt = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
+    ro, _ = both(B, O, ctx, tt, variant=variant)
+    assert int(ro["score"].max()) > 1_000_000
+    ro, _ = both(B, O, ctx, tt, variant=variant, zdrop=0)
