@@ -1447,8 +1447,8 @@ static int chain2aln_fused(bsw_ctx* ctx, const bsw_params2* P, const bsw_seed_ta
             return BSW_EINVAL;
         }
         const int64_t hmax = (int64_t)std::max(s.h0, s.init_score) + (int64_t)(ql + qr) * max_mat;
-        if (hmax > SCORE_CAP) { set_error(ctx, "seed task " + std::to_string(i) + ": score bound exceeds the 16-bit row state"); return BSW_ERANGE; }
-        *eligible = !(ql > K1_QLEN_CAP || qr > K1_QLEN_CAP || s.tlen[0] > 500000 || s.tlen[1] > 500000);
+        // beyond the 16-bit row state of the fused kernel: the host-orchestrated path (its extension calls split off K5 tasks)
+        *eligible = !(hmax > SCORE_CAP || ql > K1_QLEN_CAP || qr > K1_QLEN_CAP || s.tlen[0] > 500000 || s.tlen[1] > 500000);
         return 0;
     };
 

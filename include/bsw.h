@@ -38,7 +38,8 @@ extern "C" {
 #define BSW_EINVAL   -1   /* bad argument: null pointer, qlen<1, tlen<1, h0<1, e_ins<1, e_del<1, base code >4, ... */
 #define BSW_ECUDA    -2   /* CUDA runtime error (text via bsw_last_error) */
 #define BSW_ENOMEM   -3   /* host or device allocation failed */
-#define BSW_ERANGE   -4   /* outside the numeric envelope (sequence too long, score bound exceeds int32, ...) */
+#define BSW_ERANGE   -4   /* outside the numeric envelope: qlen > 2^20, tlen > 2^22, or h0 + qlen*(max(mat)+e_ins) >= 2^30
+                             (with option "wide" = 0: outside the 16-bit envelope h0 + qlen*max(mat) <= 32767, qlen <= 40000) */
 #define BSW_EWIRE    -5   /* malformed TBB image */
 #define BSW_EBUSY    -6   /* no free async slot / ticket not finished */
 
@@ -61,6 +62,8 @@ const char *bsw_version(void);
  * "force_kernel" {0 auto, 1 inter-task K1, 2 intra-task K2}; "k2_min_qlen" N (tasks with qlen >= N use K2 in auto mode);
  * "k2_warps" {1,4} warps per K2 task; "fused_l2" {0,1} level 2 as one fused kernel (default 1);
  * "device_plan" {1,0} sort + tile building on the device / on the host; "k2_narrow" {1,0} register path for narrow K2 rows;
+ * "wide" {1,0,2} tasks outside the 16-bit envelope of K1 / K2 (h0 + qlen*max(mat) > 32767, qlen > 40000 or tlen > 500000): 1 = the
+ * batch is split and they run on the 32-bit kernel K5 (default), 0 = the batch is refused with BSW_ERANGE, 2 = every task on K5;
  * "fpga_strict" {0,1} bsw_fpga_batch refuses tasks outside the FPGA's 8-bit envelope; "ring" {0,1} experimental K1 ring kernel
  * for long tasks (measured slower than K2, off);
  * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 0:

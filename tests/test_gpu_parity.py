@@ -483,6 +483,22 @@ def test_level2_host_orchestrated_and_long_flanks(B, O, ctx):
     assert_same(want, got2, "host-orchestrated")
 
 
+def test_level2_seeds_beyond_16_bits(B, O, ctx):
+    """Seed tasks whose chain already scores more than the 16-bit row state holds (a 60 kb read: init_score = seed
+    length x a): they leave the fused kernel for the host-orchestrated path, whose extension calls put them on K5."""
+    t = B.synth_tasks("cfg3_mixed", 2000, seed=72)
+    seeds = seeds_from_flat(t, 1000, unset_score_every=3)
+    for r in (3, 4, 5, 6, 500, 999):
+        s = dict(seeds[r]); s["h0"] = 60_000 + r
+        if s["init_score"] >= 0: s["init_score"] = 60_000 + r
+        seeds[r] = s
+    P2 = B.make_params2(B.make_params(zdrop=100), w=100, pen_clip5=5, pen_clip3=5)
+    want, _ = oracle_chain2aln(O, B, P2, seeds)
+    got = ctx.proc_element_batch(P2, seeds)
+    assert_same(want, got, "fused + 32-bit leftovers")
+    assert int(want["score"].max()) > 60_000
+
+
 def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
     """Option ring=1: long tasks run on K1R (ring row buffer); a task whose window outgrows the ring is rerun on K2."""
     ctx.set_option("ring", 1)
