@@ -62,7 +62,8 @@ __device__ __forceinline__ uint32_t k2_range_mask(int base, int a, int b)
 // reference (sx:1766-1769 / 1779,1782-1789) become two find-first/last-set on those masks.
 // Outputs: key = (row max << 16 | right-most column holding it), hlast = h of column lim-1, cb / ce = last zero cell
 // left of mj / first zero cell right of it (-1 / 0x7fffffff when there is none).
-template <int GENERIC, int CPL>
+// HI: the row-buffer word is {H hi16, E lo16} (the packed general path below), else {E hi16, H lo16}.
+template <int GENERIC, int CPL, bool HI>
 __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const uint32_t* __restrict__ qs, const int rm, const int nqw,
                                               const int j0, const int lim, const int fc, const int lane, const uint32_t trep,
                                               const uint32_t rlo, const uint32_t rhi, const int mat, const int mis,
@@ -81,7 +82,7 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
         wd[k] = live[k] ? eh[c & rm] : 0u;
         const uint32_t qw = (live[k] && (c >> 3) < nqw) ? qs[c >> 3] : 0u;
         const uint32_t nib = (qw >> (4 * (c & 7))) & 15u;
-        const int M = (int)(wd[k] & 0xffffu), e = (int)(wd[k] >> 16);
+        const int M = HI ? (int)(wd[k] >> 16) : (int)(wd[k] & 0xffffu), e = HI ? (int)(wd[k] & 0xffffu) : (int)(wd[k] >> 16);
         const int sc = k2_score<GENERIC>(GENERIC ? nib : (nib ^ (trep & 15u)), mat, mis, rlo, rhi);
         hh[k] = add_max(M, sc, e);                                                 // sx:1797,1798
         int g = add_max_relu(hh[k], -oe_ins, 0);                                   // sx:1863,1865 with h >= hh
@@ -106,7 +107,7 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
         u -= e_ins;
         h[k] = imax(hh[k], f);                                                     // sx:1809
         const int t = add_max_relu(h[k], -oe_del, 0);                              // sx:1866,1862
-        enew[k] = add_max_s16x2(wd[k], ce_pack, (uint32_t)t << 16);                // {max(e-e_del,t), 0}  sx:1770-1771
+        enew[k] = add_max_s16x2(wd[k], ce_pack, HI ? (uint32_t)t : ((uint32_t)t << 16));   // E half: max(e-e_del,t), H half: 0  sx:1770-1771
         if (live[k]) key = imax(key, h[k] * 65536 + c0 + k);                       // sx:1808,1816
     }
     int hleft = __shfl_up_sync(0xffffffffu, h[CPL - 1], 1);
@@ -116,7 +117,7 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
         const int c = c0 + k;
         if (c <= lim) {                                                            // cells and the end slot eh[lim] = {h1, 0} (sx:1775,1904,1776)
             const int h1 = (c == j0) ? fc : (k ? h[k - 1] : hleft);
-            eh[c & rm] = (c < lim ? enew[k] : 0u) | (uint32_t)h1;
+            eh[c & rm] = (c < lim ? enew[k] : 0u) | (HI ? ((uint32_t)h1 << 16) : (uint32_t)h1);
         }
     }
     key = __reduce_max_sync(0xffffffffu, key);
@@ -201,14 +202,30 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     const int oe_del = A.p.o_del + A.p.e_del, oe_ins = A.p.o_ins + A.p.e_ins;
     const int zdrop = A.p.zdrop;
     const int mat = A.p.match, mis = -A.p.mismatch;
-    const uint32_t ce_pack = 0x8000u | ((uint32_t)(-e_del) << 16);
+    // One warp per task, V1: the packed cell of K1 (bsw_k1_core.cuh) -- the row-buffer word is {H hi16, E lo16}, H / F / the
+    // running maxima stay in the high half of a register with a zero low half, and every step of the recurrence is one
+    // 16x2 add-max.  The other instantiations keep {E hi16, H lo16} and the scalar cell.
+    constexpr bool HI = (VARIANT == 1 && K2_WARPS == 1);
+    const uint32_t ce_pack = HI ? (0x80000000u | ((uint32_t)(-e_del) & 0xffffu)) : (0x8000u | ((uint32_t)(-e_del) << 16));
     const int e8 = 8 * e_ins, e256 = K2_GROUP * e_ins;
+    uint32_t c_mis = ((uint32_t)(GENERIC ? 0 : mis) << 16) | 0x8000u;        // {-b (or 0), -32768}
+    uint32_t c_noe_del = (uint32_t)(-oe_del) << 16;                          // {-oe_del, 0}
+    uint32_t c_noe_ins = (uint32_t)(-oe_ins) << 16;                          // {-oe_ins, 0}
+    uint32_t c_ne_ins = (uint32_t)(-e_ins) << 16;                            // {-e_ins, 0}
+    uint32_t zero = A.p.zero;                                                // 0, opaque to ptxas
+    uint32_t mul4[4];                                                        // (a+b) << (16 - 4k): match bit 4k -> +(a+b) in the H half
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mul4[k] = (uint32_t)(mat - mis) << (16 - 4 * k);
+    if (HI) {
+        asm volatile("" : "+r"(c_mis), "+r"(c_noe_del), "+r"(c_noe_ins), "+r"(c_ne_ins), "+r"(zero));
+        asm volatile("" : "+r"(mul4[0]), "+r"(mul4[1]), "+r"(mul4[2]), "+r"(mul4[3]));
+    }
 
     // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
     for (int j = tid; j < rcap + 8; j += K2_NT) {
         int hv = (j == 0) ? h0 : imax(h0 - A.p.o_ins - j * e_ins, 0);
         if (j > qlen) hv = 0;
-        eh[j] = (uint32_t)hv;
+        eh[j] = HI ? ((uint32_t)hv << 16) : (uint32_t)hv;
     }
     __syncthreads();                                   // mbarrier init + first row visible to every warp
     if (!ring) {
@@ -256,9 +273,9 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         const bool narrow = VARIANT == 1 && K2_WARPS == 1 && A.k2_narrow && lim - j0 < 64;           // warp-uniform
         if (narrow) {
             if (lim - j0 < 32)
-                k2_narrow_row<GENERIC, 1>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
+                k2_narrow_row<GENERIC, 1, HI>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
             else
-                k2_narrow_row<GENERIC, 2>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
+                k2_narrow_row<GENERIC, 2, HI>(eh, qs, rm, nqw, j0, lim, fc, lane, trep, rlo, rhi, mat, mis, e_ins, oe_ins, oe_del, ce_pack, key, h1, cb, ce);
             __syncwarp();                                                          // the row buffer is read by other lanes in the next row
         } else {
         int carry = 0;            // f entering the first column of the round
@@ -267,6 +284,9 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         // registers and the narrowing below needs no pass over shared memory
         const bool single = VARIANT == 1 && K2_WARPS == 1 && lim - (j0 & ~7) < K2_GROUP;
         uint32_t zlast = 0;
+        uint32_t hq[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };    // packed path: the last round's cells {h, 0}, kept for the masked arg-max below
+        uint32_t hcarry_pk = (uint32_t)fc << 16;
+        int keyprev = -1, jl_last = 0;
         // rounds start at the window (rounded down to a lane's 8 columns), not at a 256-column boundary: the live window
         // of a 1-10 kb PacBio-like task is ~200 columns wide (tools: 3.2 M rows, mean 203, 99 % below 384), and an aligned
         // group would split about half of those rows into two rounds
@@ -278,6 +298,91 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             const bool full = (lo < 0) && (hi >= 8);            // lo == 0: the lane holds the first live cell (its left neighbour is fc)
             const int klo = imax(lo, 0), khi = imin(hi, 8);
             const uint32_t livebits = khi > klo ? ((0xffu >> (8 - khi)) & (0xffu << klo)) : 0u;     // bit k: column jl + k is a cell of this row
+            if constexpr (HI) {
+                // ---- packed cell (one warp, V1) ----
+                keyprev = key;
+                jl_last = jl;
+                if (rbase != j0) {
+                    // first round of a window that does not start at a lane boundary: the columns left of j0 in lane 0 must not
+                    // feed the F chain.  They are dead for good (beg is monotone), so they are zeroed in the row buffer and
+                    // their match bits dropped: such a cell computes H = E = F = 0.  (Matrix-lookup scoring resets the chain
+                    // per cell instead.)  rbase < j0 only in the first round.
+                    if (rbase < j0) {
+                        if (lane < j0 - rbase) eh[(rbase + lane) & rm] = 0u;
+                        __syncwarp();
+                    }
+                }
+                uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
+                if (hi >= 0) {
+                    wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
+                    wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
+                }
+                uint32_t wd[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
+                const uint32_t qw = (jl >> 3) < nqw ? qs[jl >> 3] : 0u;
+                uint32_t x = qw, x2 = 0;
+                if (!GENERIC) {
+                    uint32_t y = qw ^ trep;                                  // nibble == 0 <-> match
+                    y |= y >> 1; y |= y >> 2;
+                    x = ~y & 0x11111111u;                                    // match bit of column jl + k at bit 4k
+                    x &= 0xffffffffu << (4 * imax(lo, 0));
+                    x2 = x >> 16;
+                }
+                uint32_t hh[8], fl[8];
+                uint32_t run = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t Wm;
+                    if (GENERIC) Wm = (uint32_t)k1_lookup((x >> (4 * k)) & 15u, rlo, rhi) * 65536u + wd[k];
+                    else         Wm = ((k < 4 ? x : x2) & (1u << (4 * (k & 3)))) * mul4[k & 3] + wd[k];
+                    hh[k] = add_max_s16x2(Wm, c_mis, Wm << 16);                        // {max(M + s, e), 0}  sx:1797,1798
+                    const uint32_t g = add_max_s16x2(hh[k], c_noe_ins, zero);          // sx:1863,1865 with h >= hh
+                    if (GENERIC) { if (k == lo) run = 0; }
+                    fl[k] = run;
+                    run = add_max_s16x2(run, c_ne_ins, g);                             // sx:1780,1781
+                }
+                const int runi = (int)(run >> 16);
+                int P = runi + e8 * lane;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, P, d);
+                    if (lane >= d) P = imax(P, o);
+                }
+                const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
+                const int fin0 = (lane > 0) ? imax(Pex - e8 * (lane - 1), 0) : 0;
+                const int cin = imax(carry, 0);
+                const int uin = imax(fin0, cin - e8 * lane);                           // f entering this lane's first column
+                carry = __shfl_sync(0xffffffffu, imax(runi, uin - e8), 31);
+                const uint32_t upk = (uint32_t)imax(uin, -1) << 16;                    // below zero it never wins: keep it inside 16 bits
+                uint32_t t[8];
+                uint32_t nzacc = 0;
+                int lkey = -1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t f = max_s16x2(fl[k], upk + (uint32_t)k * c_ne_ins);
+                    hq[k] = max_s16x2(hh[k], f);                                       // {h, 0}  sx:1809
+                    t[k] = add_max_s16x2(hq[k], c_noe_del, zero);                      // sx:1866,1862
+                    lkey = add_max((int)hq[k], k, lkey);                               // sx:1808,1816: (h << 16) + k, ties to the right
+                    nzacc += min(hq[k], 1u) << k;
+                }
+                if (hi > 0) key = imax(key, lkey + jl);
+                const uint32_t zbits = ~nzacc & 0xffu;                                 // cells outside the window are masked by the scan's ranges
+                uint32_t hleft = __shfl_up_sync(0xffffffffu, hq[7], 1);
+                if (lane == 0) hleft = hcarry_pk;
+                hcarry_pk = __shfl_sync(0xffffffffu, hq[7], 31);
+                if (hi >= 0 && lo < 8) {
+                    uint32_t ow[8];
+                    ow[0] = add_max_s16x2(wd[0], ce_pack, pack_hi_hi(hleft, t[0]));    // {H(i, j-1), max(e - e_del, t)}  sx:1770-1771,1776
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) ow[k] = add_max_s16x2(wd[k], ce_pack, pack_hi_hi(hq[k - 1], t[k]));
+                    *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                    unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
+                    if (lo > 0) eh16[2 * (j0 & rm) + 1] = (unsigned short)fc;       // H half of column j0 (lo == 0: hleft already is fc)
+                    if (hi < 8) eh16[2 * (lim & rm)] = 0;                           // E half of the end slot (sx:1775,1904)
+                    if (!single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
+                }
+                zlast = zbits;
+            } else {
             uint32_t wd[8];
             int hh[8], fl[8], mk[VARIANT == 2 ? 8 : 1];
             int run = 0, fin0 = 0;
@@ -409,8 +514,18 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
                 zlast = zbits;
             }
             if (K2_WARPS > 1) hcarry = xhl[K2_WARPS - 1];      // only consumed when another round follows (then the last warp was active)
+            }   // scalar cell
         }
         key = __reduce_max_sync(0xffffffffu, key);
+        if (HI && (key & 0xffff) >= lim) {
+            // the packed path takes the arg-max over all eight columns of a lane; the lane that holds `lim` also holds columns
+            // right of the window, and one of them won: redo the last round's share with those columns left out (rare)
+            int mk2 = keyprev;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (jl_last + k < lim) mk2 = imax(mk2, (int)hq[k] + jl_last + k);
+            key = __reduce_max_sync(0xffffffffu, mk2);
+        }
         if (K2_WARPS > 1 && lane == 0) xkey[warp] = key;
         k2_sync<K2_WARPS>();                                               // (3) row buffer, zero bits and keys visible
         if (K2_WARPS > 1) {
@@ -418,7 +533,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
 #pragma unroll
             for (int g = 1; g < K2_WARPS; ++g) key = imax(key, xkey[g]);
         }
-        h1 = (int)(eh[lim & rm] & 0xffffu);
+        h1 = HI ? (int)(eh[lim & rm] >> 16) : (int)(eh[lim & rm] & 0xffffu);
         if (single) {
             // narrowing from the lanes' own zero bits (sx:1766-1769 / 1779,1782-1789): bit k of zlast <-> h of column jl + k is 0
             const int mjw = key & 0xffff, jl = (j0 & ~7) + 8 * lane;
