@@ -1,5 +1,6 @@
 """Randomised parity campaign on the GPU: medium-length adversarial tasks (rows long enough for the 16-cell path, ties,
-indels, N, tiny h0 / w), random scoring, V1 and V2, level 1 through the default kernel choice and K2, level 2 fused.
+indels, N, tiny h0 / w), random scoring, V1 and V2, level 1 through the default kernel choice, K2 and K5, level 2 fused,
+K4 global alignment.
 Usage: [RAW=1] python tools/fuzz_gpu.py [iterations] [first_seed]   (RAW=1: every other iteration uses registered buffers)"""
 import sys, os, time
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,6 +13,9 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ctx = B.Context()
 fails = 0
+ntask_checked = 0
+nseed_checked = 0
+nglobal_checked = 0
 t_start = time.time()
 for it in range(iters):
     rng = np.random.default_rng(777000 + seed0 + it)
@@ -33,11 +37,12 @@ for it in range(iters):
         ctx.register_host(t["qbuf"]); ctx.register_host(t["tbuf"]); ctx.set_option("raw_inputs", 1)
     for variant in (1, 2):
         ro, co = O.extend_batch(po, *flat, variant=variant)
-        for opts in (dict(), dict(force_kernel=2)) if variant == 1 else (dict(),):
+        for opts in (dict(), dict(force_kernel=2), dict(wide=2)):          # default kernel choice, K2, K5 (32-bit rows)
             ctx.set_option("variant", variant)
             for k, v in opts.items(): ctx.set_option(k, v)
             rg, cg = ctx.sw_extend_batch(p, *flat)
-            ctx.set_option("force_kernel", 0); ctx.set_option("variant", 1)
+            ctx.set_option("force_kernel", 0); ctx.set_option("variant", 1); ctx.set_option("wide", 1)
+            ntask_checked += n
             if not (np.array_equal(ro, rg) and np.array_equal(co.astype(np.int64), cg.astype(np.int64))):
                 bad = np.nonzero((ro != rg) | (co.astype(np.int64) != cg.astype(np.int64)))[0]
                 print("MISMATCH it=%d variant=%d opts=%s pk=%s first task %d: oracle %s gpu %s" % (it, variant, opts, pk, bad[0], ro[bad[0]], rg[bad[0]]), flush=True)
@@ -60,5 +65,17 @@ for it in range(iters):
     if not np.array_equal(want, got):
         bad = np.nonzero(want != got)[0]
         print("MISMATCH L2 it=%d pk=%s first seed %d: oracle %s gpu %s" % (it, pk, bad[0], want[bad[0]], got[bad[0]]), flush=True); fails += 1
-print("fuzz: %d iterations, %d failures, %.1f s" % (iters, fails, time.time() - t_start), flush=True)
+    nseed_checked += len(seeds)
+    # K4: banded global alignment + CIGAR on the first 300 (query, target) pairs, band = length difference + a random margin
+    m = min(300, n)
+    qs = [sl(t["qbuf"], t["qoff"], i) for i in range(m)]; ts = [sl(t["tbuf"], t["toff"], i) for i in range(m)]
+    ws = [abs(len(a) - len(b)) + int(rng.integers(0, 40)) for a, b in zip(qs, ts)]
+    sc, cg = ctx.global_batch(p, qs, ts, ws, max_ops=2048)
+    for i in range(m):
+        s0, c0 = O.global_align(po, qs[i], ts[i], ws[i], max_cigar=2048)
+        if s0 != sc[i] or not np.array_equal(c0, cg[i]):
+            print("MISMATCH K4 it=%d pk=%s task %d: oracle %d gpu %d" % (it, pk, i, s0, sc[i]), flush=True); fails += 1; break
+    nglobal_checked += m
+print("fuzz: %d iterations, %d failures, %.1f s; %d extension results, %d seed records, %d global alignments compared with the oracle"
+      % (iters, fails, time.time() - t_start, ntask_checked, nseed_checked, nglobal_checked), flush=True)
 sys.exit(1 if fails else 0)
