@@ -149,6 +149,132 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
     key_out = key; cb_out = cb; ce_out = ce;
 }
 
+// ---- the packed round (one warp per task, V1) ----
+// K1's cell (bsw_k1_core.cuh): the row-buffer word is {H hi16, E lo16}; H, F and the running maxima live in the high half
+// of a register with a zero low half, and every step of the recurrence is one 16x2 add-max.  Lane l owns the CPL columns
+// rbase + CPL*l + k.  CPL = 8: the general round (256 columns, rounds repeat until the window is covered); CPL = 12: windows
+// of 256..383 columns in ONE round (a third of the rows of a 1-10 kb read; a second 8-column round costs as much as the first).
+struct K2Packed { uint32_t c_mis, c_noe_del, c_noe_ins, c_ne_ins, c_eh, zero, mul4[4]; };
+
+template <int GENERIC, int CPL>
+__device__ __forceinline__ void k2_round_packed(uint32_t* eh, const uint32_t* __restrict__ qs, uint32_t* zb, const int rm, const int nqw,
+                                                const int rbase, const int j0, const int lim, const int fc, const int lane, const bool single,
+                                                const uint32_t trep, const uint32_t rlo, const uint32_t rhi, const K2Packed& C, const int e_ins,
+                                                int& carry, uint32_t& hcarry_pk, int& key, uint32_t& zlast)
+{
+    static_assert(CPL == 8 || CPL == 12, "8 or 12 columns per lane");
+    const int jl = rbase + CPL * lane;
+    const int lo = j0 - jl, hi = lim - jl;                  // columns k with lo <= k < hi are cells of this row
+    const int eC = CPL * e_ins;
+    if (rbase < j0) {
+        // first round of a window that does not start at a lane boundary: the columns left of j0 in lane 0 must not feed
+        // the F chain.  They are dead for good (beg is monotone), so they are zeroed in the row buffer and their match
+        // bits dropped: such a cell computes H = E = F = 0.  (Matrix-lookup scoring resets the chain per cell instead.)
+        if (lane < j0 - rbase) eh[(rbase + lane) & rm] = 0u;
+        __syncwarp();
+    }
+    uint32_t wd[CPL];
+    {
+        uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa, wc = wa;
+        if (hi >= 0) {                                      // lanes right of the window read nothing (their columns may lie past the row buffer)
+            wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
+            wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
+            if (CPL == 12) wc = *reinterpret_cast<const uint4*>(eh + ((jl + 8) & rm));      // a 12-column lane may straddle the end of the ring
+            if (CPL == 12) wb = *reinterpret_cast<const uint4*>(eh + ((jl + 4) & rm));
+        }
+        wd[0] = wa.x; wd[1] = wa.y; wd[2] = wa.z; wd[3] = wa.w; wd[4] = wb.x; wd[5] = wb.y; wd[6] = wb.z; wd[7] = wb.w;
+        if (CPL == 12) { wd[8] = wc.x; wd[9] = wc.y; wd[10] = wc.z; wd[11] = wc.w; }
+    }
+    // query nibbles of the lane's columns: xa = columns 0..7, xb = columns 8..11 (CPL 12: a lane starts at nibble 0 or 4 of a word)
+    uint32_t xa, xb = 0;
+    {
+        const int qi = jl >> 3;
+        const uint32_t q0 = qi < nqw ? qs[qi] : 0u;
+        if (CPL == 8) xa = q0;
+        else {
+            const uint32_t q1 = qi + 1 < nqw ? qs[qi + 1] : 0u;
+            const int sh = 4 * (jl & 7);
+            xa = funnel_r(q0, q1, sh);
+            xb = q1 >> sh;
+        }
+    }
+    uint32_t ma0 = 0, ma1 = 0, mb = 0;                      // FAST: match bit of column k at bit 4*(k&3) of ma0 (k<4) / ma1 (k<8) / mb
+    if (!GENERIC) {
+        const uint32_t live = 0xffffffffu << (4 * imax(imin(lo, 8), 0));
+        uint32_t y = xa ^ trep;
+        y |= y >> 1; y |= y >> 2;
+        ma0 = ~y & 0x11111111u & live;
+        ma1 = ma0 >> 16;
+        if (CPL == 12) {
+            uint32_t z = xb ^ trep;
+            z |= z >> 1; z |= z >> 2;
+            mb = ~z & 0x1111u;                              // lo <= 7: columns 8..11 are never left of j0
+        }
+    }
+    uint32_t hh[CPL], fl[CPL];
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        uint32_t Wm;
+        if (GENERIC) Wm = (uint32_t)k1_lookup(((k < 8 ? xa : xb) >> (4 * (k & 7))) & 15u, rlo, rhi) * 65536u + wd[k];
+        else         Wm = ((k < 4 ? ma0 : (k < 8 ? ma1 : mb)) & (1u << (4 * (k & 3)))) * C.mul4[k & 3] + wd[k];
+        hh[k] = add_max_s16x2(Wm, C.c_mis, Wm << 16);                              // {max(M + s, e), 0}  sx:1797,1798
+        const uint32_t g = add_max_s16x2(hh[k], C.c_noe_ins, C.zero);              // sx:1863,1865 with h >= hh
+        if (GENERIC) { if (k == lo) run = 0; }
+        fl[k] = run;
+        run = add_max_s16x2(run, C.c_ne_ins, g);                                   // sx:1780,1781
+    }
+    // carries across lanes: prefix max of run[l] + CPL*e_ins*l
+    const int runi = (int)(run >> 16);
+    int P = runi + eC * lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, P, d);
+        if (lane >= d) P = imax(P, o);
+    }
+    const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
+    const int fin0 = (lane > 0) ? imax(Pex - eC * (lane - 1), 0) : 0;
+    const int cin = imax(carry, 0);
+    const int uin = imax(fin0, cin - eC * lane);                                   // f entering this lane's first column
+    carry = __shfl_sync(0xffffffffu, imax(runi, uin - eC), 31);
+    const uint32_t upk = (uint32_t)imax(uin, -1) << 16;                            // below zero it never wins: keep it inside 16 bits
+    uint32_t hq[CPL], t[CPL];
+    uint32_t nzacc = 0;
+    int lkey = -1;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const uint32_t f = max_s16x2(fl[k], upk + (uint32_t)k * C.c_ne_ins);
+        hq[k] = max_s16x2(hh[k], f);                                               // {h, 0}  sx:1809
+        t[k] = add_max_s16x2(hq[k], C.c_noe_del, C.zero);                          // sx:1866,1862
+        lkey = add_max((int)hq[k], k, lkey);                                       // sx:1808,1816: (h << 16) + k, ties to the right
+        nzacc += min(hq[k], 1u) << k;
+    }
+    // arg-max over ALL the lane's columns: a column right of the window can only win in the lane that holds `lim`; the
+    // caller notices (column >= lim) and redoes the arg-max of this round from the row buffer
+    if (hi > 0) key = imax(key, lkey + jl);
+    const uint32_t zbits = ~nzacc & ((1u << CPL) - 1u);                            // cells outside the window are masked by the scan's ranges
+    uint32_t hleft = __shfl_up_sync(0xffffffffu, hq[CPL - 1], 1);
+    if (lane == 0) hleft = hcarry_pk;
+    hcarry_pk = __shfl_sync(0xffffffffu, hq[CPL - 1], 31);
+    if (hi >= 0 && lo < CPL) {
+        // every lane that touches [j0, lim] stores its words; a boundary lane patches two of them afterwards: the first
+        // cell's left neighbour is the first-column value fc, the end slot eh[lim] is {h1, 0} (sx:1775,1904,1776); what
+        // lands left of j0 or right of lim is never read
+        uint32_t ow[CPL];
+        ow[0] = add_max_s16x2(wd[0], C.c_eh, pack_hi_hi(hleft, t[0]));             // {H(i, j-1), max(e - e_del, t)}  sx:1770-1771,1776
+#pragma unroll
+        for (int k = 1; k < CPL; ++k) ow[k] = add_max_s16x2(wd[k], C.c_eh, pack_hi_hi(hq[k - 1], t[k]));
+        *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(eh + ((jl + 4) & rm)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        if (CPL == 12) *reinterpret_cast<uint4*>(eh + ((jl + 8) & rm)) = make_uint4(ow[8], ow[9], ow[10], ow[11]);
+        unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
+        if (lo > 0) eh16[2 * (j0 & rm) + 1] = (unsigned short)fc;                  // H half of column j0 (lo == 0: hleft already is fc)
+        if (hi < CPL) eh16[2 * (lim & rm)] = 0;                                    // E half of the end slot
+        if (CPL == 8 && !single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
+    }
+    zlast = zbits;
+}
+
 template <int NW> __device__ __forceinline__ void k2_sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
 
 // VARIANT 1 = the RTL's recurrence, 2 = upstream BWA's (SURVEY appendix B "V2 deltas"): the zero guard on M, gap opens
@@ -185,7 +311,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     uint32_t* qsm = reinterpret_cast<uint32_t*>(smem_raw + K2_HDR_BYTES);         // qcap/8 words (+ pad), unused in ring mode
     const uint32_t* qs = ring ? (A.arena + (size_t)hd.qoff16 * 4u) : qsm;
     uint32_t* zb = qsm + (ring ? 0 : (qcap >> 3)) + 4;                            // rcap/32 words of zero bits
-    uint32_t* eh = zb + (rcap >> 5) + 4;                                          // rcap + 8 words
+    uint32_t* eh = zb + (rcap >> 5) + 4;                                          // rcap + 16 words
     eh = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(eh) + 15) & ~(uintptr_t)15);
 
     if (tid == 0 && !ring) {
@@ -208,21 +334,22 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     constexpr bool HI = (VARIANT == 1 && K2_WARPS == 1);
     const uint32_t ce_pack = HI ? (0x80000000u | ((uint32_t)(-e_del) & 0xffffu)) : (0x8000u | ((uint32_t)(-e_del) << 16));
     const int e8 = 8 * e_ins, e256 = K2_GROUP * e_ins;
-    uint32_t c_mis = ((uint32_t)(GENERIC ? 0 : mis) << 16) | 0x8000u;        // {-b (or 0), -32768}
-    uint32_t c_noe_del = (uint32_t)(-oe_del) << 16;                          // {-oe_del, 0}
-    uint32_t c_noe_ins = (uint32_t)(-oe_ins) << 16;                          // {-oe_ins, 0}
-    uint32_t c_ne_ins = (uint32_t)(-e_ins) << 16;                            // {-e_ins, 0}
-    uint32_t zero = A.p.zero;                                                // 0, opaque to ptxas
-    uint32_t mul4[4];                                                        // (a+b) << (16 - 4k): match bit 4k -> +(a+b) in the H half
+    K2Packed PK;
+    PK.c_mis = ((uint32_t)(GENERIC ? 0 : mis) << 16) | 0x8000u;                  // {-b (or 0), -32768}
+    PK.c_noe_del = (uint32_t)(-oe_del) << 16;                                    // {-oe_del, 0}
+    PK.c_noe_ins = (uint32_t)(-oe_ins) << 16;                                    // {-oe_ins, 0}
+    PK.c_ne_ins = (uint32_t)(-e_ins) << 16;                                      // {-e_ins, 0}
+    PK.c_eh = 0x80000000u | ((uint32_t)(-e_del) & 0xffffu);                      // {-32768, -e_del}
+    PK.zero = A.p.zero;                                                          // 0, opaque to ptxas
 #pragma unroll
-    for (int k = 0; k < 4; ++k) mul4[k] = (uint32_t)(mat - mis) << (16 - 4 * k);
+    for (int k = 0; k < 4; ++k) PK.mul4[k] = (uint32_t)(mat - mis) << (16 - 4 * k);   // match bit 4k -> +(a+b) in the H half
     if (HI) {
-        asm volatile("" : "+r"(c_mis), "+r"(c_noe_del), "+r"(c_noe_ins), "+r"(c_ne_ins), "+r"(zero));
-        asm volatile("" : "+r"(mul4[0]), "+r"(mul4[1]), "+r"(mul4[2]), "+r"(mul4[3]));
+        asm volatile("" : "+r"(PK.c_mis), "+r"(PK.c_noe_del), "+r"(PK.c_noe_ins), "+r"(PK.c_ne_ins), "+r"(PK.c_eh), "+r"(PK.zero));
+        asm volatile("" : "+r"(PK.mul4[0]), "+r"(PK.mul4[1]), "+r"(PK.mul4[2]), "+r"(PK.mul4[3]));
     }
 
     // first row: eh[j].h = H(-1, j-1), all e = 0 (sx:1818; 1979,1957,1974; 1975-1978,1821)
-    for (int j = tid; j < rcap + 8; j += K2_NT) {
+    for (int j = tid; j < rcap + 16; j += K2_NT) {
         int hv = (j == 0) ? h0 : imax(h0 - A.p.o_ins - j * e_ins, 0);
         if (j > qlen) hv = 0;
         eh[j] = HI ? ((uint32_t)hv << 16) : (uint32_t)hv;
@@ -282,11 +409,19 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         int hcarry = fc;          // h of the column left of the round
         // one warp, one round (the window fits 256 columns from j0 & ~7 -- nearly every row): the zero bits stay in
         // registers and the narrowing below needs no pass over shared memory
-        const bool single = VARIANT == 1 && K2_WARPS == 1 && lim - (j0 & ~7) < K2_GROUP;
+        const int span = lim - (j0 & ~7);
+        const bool wide12 = HI && span >= K2_GROUP && span < 12 * 32;          // warp-uniform: one round of 12 columns per lane
+        const bool single = VARIANT == 1 && K2_WARPS == 1 && (span < K2_GROUP || wide12);
         uint32_t zlast = 0;
-        uint32_t hq[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };    // packed path: the last round's cells {h, 0}, kept for the masked arg-max below
         uint32_t hcarry_pk = (uint32_t)fc << 16;
-        int keyprev = -1, jl_last = 0;
+        int keyprev = -1, jl_last = 0, cpl_last = 8;
+        if constexpr (HI) {
+            if (wide12) {
+                jl_last = (j0 & ~7) + 12 * lane; cpl_last = 12;
+                k2_round_packed<GENERIC, 12>(eh, qs, zb, rm, nqw, j0 & ~7, j0, lim, fc, lane, true, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
+            }
+        }
+        if (!wide12)
         // rounds start at the window (rounded down to a lane's 8 columns), not at a 256-column boundary: the live window
         // of a 1-10 kb PacBio-like task is ~200 columns wide (tools: 3.2 M rows, mean 203, 99 % below 384), and an aligned
         // group would split about half of those rows into two rounds
@@ -299,89 +434,8 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             const int klo = imax(lo, 0), khi = imin(hi, 8);
             const uint32_t livebits = khi > klo ? ((0xffu >> (8 - khi)) & (0xffu << klo)) : 0u;     // bit k: column jl + k is a cell of this row
             if constexpr (HI) {
-                // ---- packed cell (one warp, V1) ----
-                keyprev = key;
-                jl_last = jl;
-                if (rbase != j0) {
-                    // first round of a window that does not start at a lane boundary: the columns left of j0 in lane 0 must not
-                    // feed the F chain.  They are dead for good (beg is monotone), so they are zeroed in the row buffer and
-                    // their match bits dropped: such a cell computes H = E = F = 0.  (Matrix-lookup scoring resets the chain
-                    // per cell instead.)  rbase < j0 only in the first round.
-                    if (rbase < j0) {
-                        if (lane < j0 - rbase) eh[(rbase + lane) & rm] = 0u;
-                        __syncwarp();
-                    }
-                }
-                uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
-                if (hi >= 0) {
-                    wa = *reinterpret_cast<const uint4*>(eh + (jl & rm));
-                    wb = *reinterpret_cast<const uint4*>(eh + (jl & rm) + 4);
-                }
-                uint32_t wd[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
-                const uint32_t qw = (jl >> 3) < nqw ? qs[jl >> 3] : 0u;
-                uint32_t x = qw, x2 = 0;
-                if (!GENERIC) {
-                    uint32_t y = qw ^ trep;                                  // nibble == 0 <-> match
-                    y |= y >> 1; y |= y >> 2;
-                    x = ~y & 0x11111111u;                                    // match bit of column jl + k at bit 4k
-                    x &= 0xffffffffu << (4 * imax(lo, 0));
-                    x2 = x >> 16;
-                }
-                uint32_t hh[8], fl[8];
-                uint32_t run = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    uint32_t Wm;
-                    if (GENERIC) Wm = (uint32_t)k1_lookup((x >> (4 * k)) & 15u, rlo, rhi) * 65536u + wd[k];
-                    else         Wm = ((k < 4 ? x : x2) & (1u << (4 * (k & 3)))) * mul4[k & 3] + wd[k];
-                    hh[k] = add_max_s16x2(Wm, c_mis, Wm << 16);                        // {max(M + s, e), 0}  sx:1797,1798
-                    const uint32_t g = add_max_s16x2(hh[k], c_noe_ins, zero);          // sx:1863,1865 with h >= hh
-                    if (GENERIC) { if (k == lo) run = 0; }
-                    fl[k] = run;
-                    run = add_max_s16x2(run, c_ne_ins, g);                             // sx:1780,1781
-                }
-                const int runi = (int)(run >> 16);
-                int P = runi + e8 * lane;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, P, d);
-                    if (lane >= d) P = imax(P, o);
-                }
-                const int Pex = __shfl_up_sync(0xffffffffu, P, 1);
-                const int fin0 = (lane > 0) ? imax(Pex - e8 * (lane - 1), 0) : 0;
-                const int cin = imax(carry, 0);
-                const int uin = imax(fin0, cin - e8 * lane);                           // f entering this lane's first column
-                carry = __shfl_sync(0xffffffffu, imax(runi, uin - e8), 31);
-                const uint32_t upk = (uint32_t)imax(uin, -1) << 16;                    // below zero it never wins: keep it inside 16 bits
-                uint32_t t[8];
-                uint32_t nzacc = 0;
-                int lkey = -1;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t f = max_s16x2(fl[k], upk + (uint32_t)k * c_ne_ins);
-                    hq[k] = max_s16x2(hh[k], f);                                       // {h, 0}  sx:1809
-                    t[k] = add_max_s16x2(hq[k], c_noe_del, zero);                      // sx:1866,1862
-                    lkey = add_max((int)hq[k], k, lkey);                               // sx:1808,1816: (h << 16) + k, ties to the right
-                    nzacc += min(hq[k], 1u) << k;
-                }
-                if (hi > 0) key = imax(key, lkey + jl);
-                const uint32_t zbits = ~nzacc & 0xffu;                                 // cells outside the window are masked by the scan's ranges
-                uint32_t hleft = __shfl_up_sync(0xffffffffu, hq[7], 1);
-                if (lane == 0) hleft = hcarry_pk;
-                hcarry_pk = __shfl_sync(0xffffffffu, hq[7], 31);
-                if (hi >= 0 && lo < 8) {
-                    uint32_t ow[8];
-                    ow[0] = add_max_s16x2(wd[0], ce_pack, pack_hi_hi(hleft, t[0]));    // {H(i, j-1), max(e - e_del, t)}  sx:1770-1771,1776
-#pragma unroll
-                    for (int k = 1; k < 8; ++k) ow[k] = add_max_s16x2(wd[k], ce_pack, pack_hi_hi(hq[k - 1], t[k]));
-                    *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    *reinterpret_cast<uint4*>(eh + (jl & rm) + 4) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-                    unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
-                    if (lo > 0) eh16[2 * (j0 & rm) + 1] = (unsigned short)fc;       // H half of column j0 (lo == 0: hleft already is fc)
-                    if (hi < 8) eh16[2 * (lim & rm)] = 0;                           // E half of the end slot (sx:1775,1904)
-                    if (!single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
-                }
-                zlast = zbits;
+                keyprev = key; jl_last = jl; cpl_last = 8;
+                k2_round_packed<GENERIC, 8>(eh, qs, zb, rm, nqw, rbase, j0, lim, fc, lane, single, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
             } else {
             uint32_t wd[8];
             int hh[8], fl[8], mk[VARIANT == 2 ? 8 : 1];
@@ -517,17 +571,19 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             }   // scalar cell
         }
         key = __reduce_max_sync(0xffffffffu, key);
-        if (HI && (key & 0xffff) >= lim) {
-            // the packed path takes the arg-max over all eight columns of a lane; the lane that holds `lim` also holds columns
-            // right of the window, and one of them won: redo the last round's share with those columns left out (rare)
-            int mk2 = keyprev;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (jl_last + k < lim) mk2 = imax(mk2, (int)hq[k] + jl_last + k);
-            key = __reduce_max_sync(0xffffffffu, mk2);
-        }
         if (K2_WARPS > 1 && lane == 0) xkey[warp] = key;
         k2_sync<K2_WARPS>();                                               // (3) row buffer, zero bits and keys visible
+        if (HI && (key & 0xffff) >= lim) {
+            // the packed round takes the arg-max over all the columns of a lane; the lane that holds `lim` also holds columns
+            // right of the window, and one of them won: redo the last round's share with those columns left out, from the
+            // row buffer (slot c + 1 holds h of column c).  Rare.
+            int mk2 = keyprev;
+            for (int k = 0; k < cpl_last; ++k) {
+                const int c = jl_last + k;
+                if (c >= j0 && c < lim) mk2 = imax(mk2, (int)(eh[(c + 1) & rm] & 0xffff0000u) + c);
+            }
+            key = __reduce_max_sync(0xffffffffu, mk2);
+        }
         if (K2_WARPS > 1) {
             key = xkey[0];
 #pragma unroll
@@ -536,7 +592,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         h1 = HI ? (int)(eh[lim & rm] >> 16) : (int)(eh[lim & rm] & 0xffffu);
         if (single) {
             // narrowing from the lanes' own zero bits (sx:1766-1769 / 1779,1782-1789): bit k of zlast <-> h of column jl + k is 0
-            const int mjw = key & 0xffff, jl = (j0 & ~7) + 8 * lane;
+            const int mjw = key & 0xffff, jl = (j0 & ~7) + cpl_last * lane;
             const uint32_t za = zlast & k2_range_mask(jl, j0, mjw - 1);
             const uint32_t ze = zlast & k2_range_mask(jl, mjw + 1, lim - 1);
             cb = __reduce_max_sync(0xffffffffu, za ? jl + 31 - __clz(za) : -1);
@@ -617,7 +673,7 @@ size_t k2_smem_bytes(int qmax, int wmax)
     const size_t qcap = ((size_t)qmax + 1 + K2_GROUP - 1) & ~(size_t)(K2_GROUP - 1);
     const bool ring = qcap > (size_t)K2_RING && 2 * (size_t)wmax + 1 + 2 * K2_GROUP <= (size_t)K2_RING;
     const size_t rcap = ring ? (size_t)K2_RING : qcap;
-    return (size_t)K2_HDR_BYTES + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
+    return (size_t)K2_HDR_BYTES + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 16) * 4u + 16u;
 }
 
 template <int GENERIC, int NW, int VARIANT>
