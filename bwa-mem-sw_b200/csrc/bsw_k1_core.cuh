@@ -22,6 +22,11 @@
 //     f   = max(f + {-e_ins, 0}, t)                  VIADDMNMX.S16x2                           sx:1863,1865,1780-1781
 //     key = max(key, h + k)                          VIADDMNMX  (h is already h<<16: row max + right-most column) sx:1808,1816
 // = 8 ALU-pipe + 2 FMA-pipe instructions, 1 LDS, 1 STS per cell for 13 algorithmic integer ops.
+// The loop-carried chain of a row is f -> h -> t -> f (three dependent instructions per cell).  Opening the gap from hh
+// instead (max(f - e_ins, h - oe_ins) = max(f - e_ins, hh - oe_ins), since f - oe_ins <= f - e_ins) cuts it to one, but
+// with symmetric gap penalties it costs a ninth ALU instruction (t no longer serves both gaps): measured 1 110 against
+// 1 135-1 142 GCUPS on 1 M x 150 bp (r02) -- the kernel is bound by ALU issue, not by the chain.  The asymmetric path
+// needs its own instruction anyway and takes it from hh.
 //
 // Band narrowing (V1).  The reference recomputes [beg,end) after every row by scanning the stored
 // row for the run of non-zero H around mj (sw_pe_array_sw_extend.v:1766-1769,1779,1782-1789).  A
@@ -279,7 +284,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             const uint32_t t = add_max_s16x2(h, c_noe_del, zero);                                    \
             const uint32_t nw = add_max_s16x2((W), c_eh, pack_hi_hi(h1, t));                         \
             if (SYM) f = add_max_s16x2(f, c_ne_ins, t);                                              \
-            else     f = add_max_s16x2(f, c_ne_ins, add_max_s16x2(h, c_noe_ins, zero));              \
+            else     f = add_max_s16x2(f, c_ne_ins, add_max_s16x2(hh, c_noe_ins, zero));             \
             if (LIVE) { ehp[(K) * K1_S] = nw; ckey = (K) ? add_max((int)h, (K), ckey) : (int)h; h1 = h; } \
         }
 
