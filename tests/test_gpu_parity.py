@@ -604,10 +604,12 @@ def test_scores_at_the_16_bit_cap(B, O, ctx, variant):
     t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.full(len(h0), 100, np.int32))
     ro, _ = both(B, O, ctx, t, variant=variant, zdrop=0)
     assert int(ro["score"].max()) == 32767
+    both(B, O, ctx, t, variant=variant, opts={"force_kernel": 2}, zdrop=0)                            # K2's packed cell wraps the same way
     # a=2: max(mat) = 2
     t["h0"] = np.array([32767 - 2 * len(q) for q in qs], np.int32)
     ro, _ = both(B, O, ctx, t, variant=variant, a=2, b=3, zdrop=0)
     assert int(ro["score"].max()) == 32767
+    both(B, O, ctx, t, variant=variant, opts={"force_kernel": 2}, a=2, b=3, zdrop=0)
     t["h0"][5] += 1                                                                                   # one past the cap: never wrapped --
     ctx.set_option("wide", 0)                                                                         # refused without the 32-bit kernel,
     try:
@@ -618,6 +620,26 @@ def test_scores_at_the_16_bit_cap(B, O, ctx, variant):
         ctx.set_option("wide", 1)
     ro, _ = both(B, O, ctx, t, variant=variant, a=2, b=3, zdrop=0)                                    # exact with it (that one task runs on K5)
     assert int(ro["score"].max()) == 32768
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_long_reads_at_the_16_bit_cap(B, O, ctx, variant):
+    """K2 in its own regime at the edge of the envelope: 3-8 kb near-perfect matches whose score climbs to exactly 32767
+    (h0 = 32767 - qlen), windows 250-400 columns wide (the 12-column rounds), ring row buffer."""
+    rng = np.random.default_rng(78)
+    qs, ts, h0 = [], [], []
+    for k in range(24):
+        ql = int(rng.integers(3000, 8000))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        t = np.concatenate([q, rng.integers(0, 4, 60).astype(np.uint8)])
+        if k % 2:
+            t[rng.integers(0, ql, ql // 200)] = rng.integers(0, 4)                # 0.5 % substitutions
+        qs.append(q); ts.append(t); h0.append(32767 - ql)
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.full(len(h0), 180, np.int32))
+    ro, _ = both(B, O, ctx, t, variant=variant, zdrop=0)
+    assert int(ro["score"].max()) == 32767
+    both(B, O, ctx, t, variant=variant, zdrop=100)
 
 
 @pytest.mark.parametrize("variant", [1, 2])
