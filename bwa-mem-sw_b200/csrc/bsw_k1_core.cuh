@@ -128,6 +128,24 @@ BSW_HD uint32_t pack_hi_hi(uint32_t hi_src, uint32_t lo_src)   // {hi_src[31:16]
 #endif
 }
 
+BSW_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+BSW_HD int bsw_top_bit(uint32_t x)      // index of the highest set bit, x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+BSW_HD int bsw_low_bit(uint32_t x)      // index of the lowest set bit, x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
 constexpr int K1_S = TILE_LANES;            // stride (in words) between consecutive columns / words of one lane
 constexpr int K1_QS_EXTRA = 8;              // query words per lane past nqw_max (one-hot planes need a zero block)
 constexpr int K1_KEY_NONE = -1;
@@ -181,6 +199,14 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     uint32_t c_noe_ins = (uint32_t)(-oe_ins) << 16;                          // {-oe_ins, 0}
     uint32_t c_ne_ins = (uint32_t)(-e_ins) << 16;                            // {-e_ins, 0}
     uint32_t c_eh = 0x80000000u | ((uint32_t)(-e_del) & 0xffffu);            // {-32768, -e_del}
+    // V2 opens both gaps from M = M_old + s (not from h): {s - oe, -32768} added to {M_old + (a+b)*match, e}
+    uint32_t c_mis_oed = ((uint32_t)((GENERIC ? 0 : mis) - oe_del) << 16) | 0x8000u;
+    uint32_t c_mis_oei = ((uint32_t)((GENERIC ? 0 : mis) - oe_ins) << 16) | 0x8000u;
+    uint32_t mul4[4];                                                        // V2 (query kept as nibbles): match bit 4k -> +(a+b) in the H half
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) mul4[k] = (uint32_t)(mat - mis) << (16 - 4 * k);
     uint32_t zero = P.zero;                                                  // 0, but opaque to ptxas (else it re-materialises a zero per cell)
     uint32_t mul[8];                                                         // (a+b) << (16-k)
 #if defined(__CUDA_ARCH__)
@@ -191,6 +217,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     // keep the loop constants in ordinary registers (otherwise ptxas re-reads them from the constant bank per cell)
     asm volatile("" : "+r"(c_mis), "+r"(c_noe_del), "+r"(c_noe_ins), "+r"(c_ne_ins), "+r"(c_eh), "+r"(zero));
     asm volatile("" : "+r"(mul[0]), "+r"(mul[1]), "+r"(mul[2]), "+r"(mul[3]), "+r"(mul[4]), "+r"(mul[5]), "+r"(mul[6]), "+r"(mul[7]));
+    if (VARIANT == 2) asm volatile("" : "+r"(c_mis_oed), "+r"(c_mis_oei), "+r"(mul4[0]), "+r"(mul4[1]), "+r"(mul4[2]), "+r"(mul4[3]));
 #endif
 
     if (!prep) {
@@ -286,6 +313,46 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             if (SYM) f = add_max_s16x2(f, c_ne_ins, t);                                              \
             else     f = add_max_s16x2(f, c_ne_ins, add_max_s16x2(hh, c_noe_ins, zero));             \
             if (LIVE) { ehp[(K) * K1_S] = nw; ckey = (K) ? add_max((int)h, (K), ckey) : (int)h; h1 = h; } \
+        }
+
+        // The same cell under the V2 recurrence, for chunks whose H are all non-zero (the zero guard "M ? M + s : 0" is then
+        // vacuous): both gap opens come from M = M_old + s, which is Wm plus a constant -- off the F chain.  XB = match bits at
+        // bit 4k (XB2 = XB >> 16 for k >= 4) or the nibbles (GENERIC).  ACC collects "stored word != 0" per column: BWA's
+        // narrowing scans for the first and last column whose h and e are not both zero.
+#define BSW_K1_FAST2(K, W, XB, XB2)                                                                  \
+        {                                                                                            \
+            uint32_t Wm;                                                                             \
+            if (GENERIC) Wm = (uint32_t)k1_lookup(((XB) >> (4 * (K))) & 15u, rlo, rhi) * 65536u + (W); \
+            else         Wm = (((K) < 4 ? (XB) : (XB2)) & (1u << (4 * ((K) & 3)))) * mul4[(K) & 3] + (W); \
+            const uint32_t hh = add_max_s16x2(Wm, c_mis, Wm << 16);                                  \
+            const uint32_t h = max_s16x2(hh, f);                                                     \
+            const uint32_t t = add_max_s16x2(Wm, c_mis_oed, zero);                                   \
+            const uint32_t nw = add_max_s16x2((W), c_eh, pack_hi_hi(h1, t));                         \
+            if (SYM) f = add_max_s16x2(f, c_ne_ins, t);                                              \
+            else     f = add_max_s16x2(f, c_ne_ins, add_max_s16x2(Wm, c_mis_oei, zero));             \
+            ehp[(K) * K1_S] = nw; ckey = (K) ? add_max((int)h, (K), ckey) : (int)h; h1 = h;          \
+            acc += (nw != 0u ? 1u : 0u) << (K);                                                      \
+        }
+
+        // ... and for chunks that do hold a zero H: the guard "M ? M + s : 0" as one unsigned minimum.  mk+ = max(M_old + s, 0)
+        // differs from the guarded value only where M_old == 0 and s > 0; (0 - (M_old << 16)) as an unsigned word is 0 there and
+        // at least 0x80010000 everywhere else, so min_u32(mk+, that) is the guard.  (A negative M_old + s behaves like 0 in
+        // everything that follows: h is a max with e, f >= 0 and both gap opens are clipped at 0.)
+#define BSW_K1_GUARD2(K, W, XB, XB2)                                                                 \
+        {                                                                                            \
+            uint32_t Wm;                                                                             \
+            if (GENERIC) Wm = (uint32_t)k1_lookup(((XB) >> (4 * (K))) & 15u, rlo, rhi) * 65536u + (W); \
+            else         Wm = (((K) < 4 ? (XB) : (XB2)) & (1u << (4 * ((K) & 3)))) * mul4[(K) & 3] + (W); \
+            const uint32_t mkp = add_max_s16x2(Wm, c_mis, zero);                                     \
+            const uint32_t mk = umin32(mkp, 0u - ((W) & 0xffff0000u));                               \
+            const uint32_t hh = max_s16x2(mk, Wm << 16);                                             \
+            const uint32_t h = max_s16x2(hh, f);                                                     \
+            const uint32_t t = add_max_s16x2(mk, c_noe_del, zero);                                   \
+            const uint32_t nw = add_max_s16x2((W), c_eh, pack_hi_hi(h1, t));                         \
+            if (SYM) f = add_max_s16x2(f, c_ne_ins, t);                                              \
+            else     f = add_max_s16x2(f, c_ne_ins, add_max_s16x2(mk, c_noe_ins, zero));             \
+            ehp[(K) * K1_S] = nw; ckey = (K) ? add_max((int)h, (K), ckey) : (int)h; h1 = h;          \
+            acc += (nw != 0u ? 1u : 0u) << (K);                                                      \
         }
 
         bool stop = false;
@@ -397,6 +464,45 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                     }
                 }
             }
+            if (VARIANT == 2 && !RING && nv >= 8) {
+                const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
+                const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
+                uint32_t zm = min3_u16x2(w0, w1, w2);
+                zm = min3_u16x2(zm, w3, w4);
+                zm = min3_u16x2(zm, w5, w6);
+                zm = min3_u16x2(zm, w7, w7);
+                uint32_t xb = x, xb2 = 0;
+                if (!GENERIC) {
+                    uint32_t y = x ^ trep;                   // nibble == 0 <-> match
+                    y |= y >> 1; y |= y >> 2;
+                    xb = ~y & 0x11111111u; xb2 = xb >> 16;
+                }
+                int ckey = K1_KEY_NONE;
+                uint32_t acc = 0;
+                if (zm >= 0x10000u) {                        // no zero H in the chunk: the zero guard never fires
+                    BSW_K1_FAST2(0, w0, xb, xb2)
+                    BSW_K1_FAST2(1, w1, xb, xb2)
+                    BSW_K1_FAST2(2, w2, xb, xb2)
+                    BSW_K1_FAST2(3, w3, xb, xb2)
+                    BSW_K1_FAST2(4, w4, xb, xb2)
+                    BSW_K1_FAST2(5, w5, xb, xb2)
+                    BSW_K1_FAST2(6, w6, xb, xb2)
+                    BSW_K1_FAST2(7, w7, xb, xb2)
+                } else {
+                    BSW_K1_GUARD2(0, w0, xb, xb2)
+                    BSW_K1_GUARD2(1, w1, xb, xb2)
+                    BSW_K1_GUARD2(2, w2, xb, xb2)
+                    BSW_K1_GUARD2(3, w3, xb, xb2)
+                    BSW_K1_GUARD2(4, w4, xb, xb2)
+                    BSW_K1_GUARD2(5, w5, xb, xb2)
+                    BSW_K1_GUARD2(6, w6, xb, xb2)
+                    BSW_K1_GUARD2(7, w7, xb, xb2)
+                }
+                mkey = imax(mkey, ckey + j);
+                if (acc) { lnz = j + bsw_top_bit(acc); fnz = imin(fnz, j + bsw_low_bit(acc)); }
+                j += 8; ehp += 8 * K1_S;
+                continue;
+            }
             // careful path: cell by cell, with the narrowing events (V1) or the V2 recurrence
             const int kmax = nv < 8 ? nv : 8;
             for (int k = 0; k < kmax; ++k, ++j, ehp += K1_S) {
@@ -427,6 +533,8 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             if (stop) break;
         }
 #undef BSW_K1_FAST
+#undef BSW_K1_FAST2
+#undef BSW_K1_GUARD2
 
         const int e_eff = lim;
         const int h1v = (int)(h1 >> 16);
