@@ -156,13 +156,13 @@ __device__ __forceinline__ void k2_narrow_row(uint32_t* __restrict__ eh, const u
 // of 256..383 columns in ONE round (a third of the rows of a 1-10 kb read; a second 8-column round costs as much as the first).
 struct K2Packed { uint32_t c_mis, c_noe_del, c_noe_ins, c_ne_ins, c_eh, zero, mul4[4]; };
 
-template <int GENERIC, int CPL>
+template <int GENERIC, int CPL, int VARIANT>
 __device__ __forceinline__ void k2_round_packed(uint32_t* eh, const uint32_t* __restrict__ qs, uint32_t* zb, const int rm, const int nqw,
                                                 const int rbase, const int j0, const int lim, const int fc, const int lane, const bool single,
                                                 const uint32_t trep, const uint32_t rlo, const uint32_t rhi, const K2Packed& C, const int e_ins,
                                                 int& carry, uint32_t& hcarry_pk, int& key, uint32_t& zlast)
 {
-    static_assert(CPL == 8 || CPL == 12, "8 or 12 columns per lane");
+    static_assert(CPL == 8 || (CPL == 12 && VARIANT == 1), "8 columns per lane, or 12 in single-round V1 rows");
     const int jl = rbase + CPL * lane;
     const int lo = j0 - jl, hi = lim - jl;                  // columns k with lo <= k < hi are cells of this row
     const int eC = CPL * e_ins;
@@ -211,16 +211,27 @@ __device__ __forceinline__ void k2_round_packed(uint32_t* eh, const uint32_t* __
             mb = ~z & 0x1111u;                              // lo <= 7: columns 8..11 are never left of j0
         }
     }
-    uint32_t hh[CPL], fl[CPL];
+    uint32_t hh[CPL], fl[CPL], t[CPL];
     uint32_t run = 0;
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         uint32_t Wm;
         if (GENERIC) Wm = (uint32_t)k1_lookup(((k < 8 ? xa : xb) >> (4 * (k & 7))) & 15u, rlo, rhi) * 65536u + wd[k];
         else         Wm = ((k < 4 ? ma0 : (k < 8 ? ma1 : mb)) & (1u << (4 * (k & 3)))) * C.mul4[k & 3] + wd[k];
-        hh[k] = add_max_s16x2(Wm, C.c_mis, Wm << 16);                              // {max(M + s, e), 0}  sx:1797,1798
-        const uint32_t g = add_max_s16x2(hh[k], C.c_noe_ins, C.zero);              // sx:1863,1865 with h >= hh
-        if (GENERIC) { if (k == lo) run = 0; }
+        uint32_t g;
+        if (VARIANT == 2) {
+            // upstream BWA: the zero guard "M ? M + s : 0" as one unsigned minimum (see BSW_K1_GUARD2 in bsw_k1_core.cuh),
+            // both gap opens from M -- so t does not wait for F either
+            const uint32_t mkp = add_max_s16x2(Wm, C.c_mis, C.zero);
+            const uint32_t mk = umin32(mkp, 0u - (wd[k] & 0xffff0000u));
+            hh[k] = max_s16x2(mk, Wm << 16);
+            g = add_max_s16x2(mk, C.c_noe_ins, C.zero);
+            t[k] = add_max_s16x2(mk, C.c_noe_del, C.zero);
+        } else {
+            hh[k] = add_max_s16x2(Wm, C.c_mis, Wm << 16);                          // {max(M + s, e), 0}  sx:1797,1798
+            g = add_max_s16x2(hh[k], C.c_noe_ins, C.zero);                         // sx:1863,1865 with h >= hh
+            if (GENERIC) { if (k == lo) run = 0; }                                 // (V2: a zeroed dead column yields M = 0 whatever the matrix says)
+        }
         fl[k] = run;
         run = add_max_s16x2(run, C.c_ne_ins, g);                                   // sx:1780,1781
     }
@@ -238,38 +249,61 @@ __device__ __forceinline__ void k2_round_packed(uint32_t* eh, const uint32_t* __
     const int uin = imax(fin0, cin - eC * lane);                                   // f entering this lane's first column
     carry = __shfl_sync(0xffffffffu, imax(runi, uin - eC), 31);
     const uint32_t upk = (uint32_t)imax(uin, -1) << 16;                            // below zero it never wins: keep it inside 16 bits
-    uint32_t hq[CPL], t[CPL];
+    uint32_t hq[CPL];
     uint32_t nzacc = 0;
     int lkey = -1;
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const uint32_t f = max_s16x2(fl[k], upk + (uint32_t)k * C.c_ne_ins);
         hq[k] = max_s16x2(hh[k], f);                                               // {h, 0}  sx:1809
-        t[k] = add_max_s16x2(hq[k], C.c_noe_del, C.zero);                          // sx:1866,1862
+        if (VARIANT == 1) t[k] = add_max_s16x2(hq[k], C.c_noe_del, C.zero);        // sx:1866,1862
         lkey = add_max((int)hq[k], k, lkey);                                       // sx:1808,1816: (h << 16) + k, ties to the right
-        nzacc += min(hq[k], 1u) << k;
+        if (VARIANT == 1) nzacc += min(hq[k], 1u) << k;
     }
     // arg-max over ALL the lane's columns: a column right of the window can only win in the lane that holds `lim`; the
     // caller notices (column >= lim) and redoes the arg-max of this round from the row buffer
     if (hi > 0) key = imax(key, lkey + jl);
-    const uint32_t zbits = ~nzacc & ((1u << CPL) - 1u);                            // cells outside the window are masked by the scan's ranges
+    uint32_t zbits = ~nzacc & ((1u << CPL) - 1u);                                  // V1: "h == 0" per column; cells outside the window are masked by the scan's ranges
     uint32_t hleft = __shfl_up_sync(0xffffffffu, hq[CPL - 1], 1);
     if (lane == 0) hleft = hcarry_pk;
     hcarry_pk = __shfl_sync(0xffffffffu, hq[CPL - 1], 31);
     if (hi >= 0 && lo < CPL) {
-        // every lane that touches [j0, lim] stores its words; a boundary lane patches two of them afterwards: the first
-        // cell's left neighbour is the first-column value fc, the end slot eh[lim] is {h1, 0} (sx:1775,1904,1776); what
-        // lands left of j0 or right of lim is never read
         uint32_t ow[CPL];
         ow[0] = add_max_s16x2(wd[0], C.c_eh, pack_hi_hi(hleft, t[0]));             // {H(i, j-1), max(e - e_del, t)}  sx:1770-1771,1776
 #pragma unroll
         for (int k = 1; k < CPL; ++k) ow[k] = add_max_s16x2(wd[k], C.c_eh, pack_hi_hi(hq[k - 1], t[k]));
-        *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        *reinterpret_cast<uint4*>(eh + ((jl + 4) & rm)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-        if (CPL == 12) *reinterpret_cast<uint4*>(eh + ((jl + 8) & rm)) = make_uint4(ow[8], ow[9], ow[10], ow[11]);
-        unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
-        if (lo > 0) eh16[2 * (j0 & rm) + 1] = (unsigned short)fc;                  // H half of column j0 (lo == 0: hleft already is fc)
-        if (hi < CPL) eh16[2 * (lim & rm)] = 0;                                    // E half of the end slot
+        if (VARIANT == 2 && !(lo < 0 && hi >= CPL)) {
+            // V2 boundary lane: exactly the cells [lo, hi) and the end slot, nothing beside them -- the zero scan may grow the
+            // window, and a later row then reads the slots next to it as they are.  First cell: H half = fc; end slot: E half = 0.
+            uint32_t nz = 0;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                if (k >= lo && k <= hi) {
+                    uint32_t v = (k == lo) ? ((ow[k] & 0x0000ffffu) | ((uint32_t)fc << 16)) : ow[k];
+                    if (k == hi) v &= 0xffff0000u;
+                    eh[(jl + k) & rm] = v;
+                    nz |= (v != 0u ? 1u : 0u) << k;
+                }
+            }
+            zbits = nz;
+        } else {
+            // every lane that touches [j0, lim] stores its words; a V1 boundary lane patches two of them afterwards: the
+            // first cell's left neighbour is the first-column value fc, the end slot eh[lim] is {h1, 0} (sx:1775,1904,1776);
+            // what lands left of j0 or right of lim is never read
+            *reinterpret_cast<uint4*>(eh + (jl & rm)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *reinterpret_cast<uint4*>(eh + ((jl + 4) & rm)) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            if (CPL == 12) *reinterpret_cast<uint4*>(eh + ((jl + 8) & rm)) = make_uint4(ow[8], ow[9], ow[10], ow[11]);
+            if (VARIANT == 1) {
+                unsigned short* eh16 = reinterpret_cast<unsigned short*>(eh);
+                if (lo > 0) eh16[2 * (j0 & rm) + 1] = (unsigned short)fc;          // H half of column j0 (lo == 0: hleft already is fc)
+                if (hi < CPL) eh16[2 * (lim & rm)] = 0;                            // E half of the end slot
+            } else {
+                uint32_t nz = 0;                                                   // V2 keeps "word != 0" per column (full lane: all are cells)
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) nz += min(ow[k], 1u) << k;
+                zbits = nz;
+            }
+        }
         if (CPL == 8 && !single) reinterpret_cast<unsigned char*>(zb)[(jl & rm) >> 3] = (unsigned char)zbits;
     }
     zlast = zbits;
@@ -331,7 +365,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
     // One warp per task, V1: the packed cell of K1 (bsw_k1_core.cuh) -- the row-buffer word is {H hi16, E lo16}, H / F / the
     // running maxima stay in the high half of a register with a zero low half, and every step of the recurrence is one
     // 16x2 add-max.  The other instantiations keep {E hi16, H lo16} and the scalar cell.
-    constexpr bool HI = (VARIANT == 1 && K2_WARPS == 1);
+    constexpr bool HI = (K2_WARPS == 1);
     const uint32_t ce_pack = HI ? (0x80000000u | ((uint32_t)(-e_del) & 0xffffu)) : (0x8000u | ((uint32_t)(-e_del) << 16));
     const int e8 = 8 * e_ins, e256 = K2_GROUP * e_ins;
     K2Packed PK;
@@ -386,7 +420,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         if (VARIANT == 2 && lim - 1 > hiw) {
             // ring mode: columns the window reaches for the first time still hold what column - 2048 left there; a
             // flat row buffer would show the first-row fill (sx:1975-1978) -- put it there
-            for (int c = hiw + 1 + tid; c <= lim - 1; c += K2_NT) eh[c & rm] = (uint32_t)(c > qlen ? 0 : imax(h0 - A.p.o_ins - c * e_ins, 0));
+            for (int c = hiw + 1 + tid; c <= lim - 1; c += K2_NT) eh[c & rm] = (uint32_t)(c > qlen ? 0 : imax(h0 - A.p.o_ins - c * e_ins, 0)) << (HI ? 16 : 0);
             k2_sync<K2_WARPS>();
         }
         if (VARIANT == 2) hiw = imax(hiw, lim);
@@ -410,7 +444,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         // one warp, one round (the window fits 256 columns from j0 & ~7 -- nearly every row): the zero bits stay in
         // registers and the narrowing below needs no pass over shared memory
         const int span = lim - (j0 & ~7);
-        const bool wide12 = HI && span >= K2_GROUP && span < 12 * 32;          // warp-uniform: one round of 12 columns per lane
+        const bool wide12 = HI && VARIANT == 1 && span >= K2_GROUP && span < 12 * 32;          // warp-uniform: one round of 12 columns per lane
         const bool single = VARIANT == 1 && K2_WARPS == 1 && (span < K2_GROUP || wide12);
         uint32_t zlast = 0;
         uint32_t hcarry_pk = (uint32_t)fc << 16;
@@ -418,7 +452,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
         if constexpr (HI) {
             if (wide12) {
                 jl_last = (j0 & ~7) + 12 * lane; cpl_last = 12;
-                k2_round_packed<GENERIC, 12>(eh, qs, zb, rm, nqw, j0 & ~7, j0, lim, fc, lane, true, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
+                k2_round_packed<GENERIC, 12, 1>(eh, qs, zb, rm, nqw, j0 & ~7, j0, lim, fc, lane, true, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
             }
         }
         if (!wide12)
@@ -435,7 +469,7 @@ __global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_c
             const uint32_t livebits = khi > klo ? ((0xffu >> (8 - khi)) & (0xffu << klo)) : 0u;     // bit k: column jl + k is a cell of this row
             if constexpr (HI) {
                 keyprev = key; jl_last = jl; cpl_last = 8;
-                k2_round_packed<GENERIC, 8>(eh, qs, zb, rm, nqw, rbase, j0, lim, fc, lane, single, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
+                k2_round_packed<GENERIC, 8, VARIANT>(eh, qs, zb, rm, nqw, rbase, j0, lim, fc, lane, single, trep, rlo, rhi, PK, e_ins, carry, hcarry_pk, key, zlast);
             } else {
             uint32_t wd[8];
             int hh[8], fl[8], mk[VARIANT == 2 ? 8 : 1];
