@@ -318,7 +318,7 @@ template <int NW> __device__ __forceinline__ void k2_sync() { if (NW == 1) __syn
 // cells [j0, lim] (V1 may scribble over the columns next to the window, nobody reads them), and in ring mode a column
 // that was never written is given its first-row value before the first row that can read it.
 template <int GENERIC, int K2_WARPS, int VARIANT>
-__global__ void __launch_bounds__(32 * K2_WARPS) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
+__global__ void __launch_bounds__(32 * K2_WARPS, K2_WARPS == 1 ? 24 : 1) k2_extend_kernel(const __grid_constant__ LaunchArgs A)
 {
     constexpr int K2_NT = 32 * K2_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
