@@ -157,11 +157,8 @@ struct WideArgs {
 };
 
 constexpr int STATUS_OK = 0;
-constexpr int STATUS_OVERFLOW = 1;  // K1R: the live window outgrew the ring; the host reruns the task on K2
 constexpr int STATUS_HAS_N = 2;     // raw mode: the task holds an N and ran on the +a/-b kernel; the host reruns it with matrix lookup
 constexpr int STATUS_BAD_CODE = 3;  // raw mode: a base code above 4
 constexpr uint32_t SLOT_HAS_N = 1u, SLOT_BAD_CODE = 2u;
-constexpr int K1R_RING = 512;       // columns of K1R's row ring
-constexpr uint32_t TILE_ONEHOT = 0x8000u;   // TileHdr.nqw_ntw bit 15: the query block holds match planes (K0 builds them)
 
 }  // namespace bsw

@@ -333,7 +333,6 @@ int enqueue_launches(bsw_ctx* ctx, Slot& s, const DevParams& dp, int sym, int va
         const size_t lane_ix = nl % (size_t)(nuse + 1);
         cudaStream_t st = (spread && lane_ix) ? s.side[lane_ix - 1] : s.stream;
         cudaError_t e = (L.kind == 1) ? k1_launch(a, variant, L.generic, sym, st)
-                      : (L.kind == 4) ? k1r_launch(a, L.generic, sym, st)
                                       : k2_launch(a, L.generic, ctx->k2_warps, variant, st);
         if (e != cudaSuccess) return cuda_fail(ctx, e, L.kind == 1 ? "K1 launch" : "K2 launch");
         ++nl;
@@ -520,7 +519,7 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
                      bool packed2, std::vector<size_t>* rerun_n)
 {
     const double t0 = now_ms();
-    if (opt.force_kernel == 2 || opt.ring || count == 0) return 1;
+    if (opt.force_kernel == 2 || count == 0) return 1;
     int rc;
     const size_t max_tiles = count / TILE_LANES + 8;
     const size_t off_param = 0, off_src = count * sizeof(SlotParam);
@@ -646,8 +645,7 @@ int slot_submit_lean(bsw_ctx* ctx, Slot& s, const FlatSrc& F, size_t first, size
     return 0;
 }
 
-int slot_collect_lean(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow,
-                      std::vector<size_t>* rerun_n)
+int slot_collect_lean(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* rerun_n)
 {
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
     s.busy = false; s.lean = false;
@@ -673,8 +671,7 @@ int slot_collect_lean(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, L
     }
     for (uint32_t k = 0; k < nflag; ++k) {
         const uint32_t status = list[k] >> 28; const size_t t = first + (list[k] & 0x0fffffffu);
-        if (status == STATUS_OVERFLOW) overflow->push_back(t);
-        else if (status == STATUS_HAS_N) rerun_n->push_back(t);
+        if (status == STATUS_HAS_N) rerun_n->push_back(t);
         else if (status == STATUS_BAD_CODE) { set_error(ctx, "task " + std::to_string(t) + ": invalid (base code > 4)"); return BSW_EINVAL; }
         else { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
     }
@@ -683,11 +680,10 @@ int slot_collect_lean(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, L
 }
 
 // Wait for the slot's chunk and scatter its results to out[first + task].
-int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* overflow,
-                 std::vector<size_t>* rerun_n)
+int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalStats* st, std::vector<size_t>* rerun_n)
 {
     if (!s.busy) return 0;
-    if (s.lean) return slot_collect_lean(ctx, s, out, cells, st, overflow, rerun_n);
+    if (s.lean) return slot_collect_lean(ctx, s, out, cells, st, rerun_n);
     CUDA_TRY(ctx, cudaEventSynchronize(s.ev_done));
     s.busy = false;
     float ms = 0.f;
@@ -705,7 +701,6 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
     // the kernels wrote every record at its task's index: a sequential pass
     for (size_t t = 0; t < count; ++t) {
         const SlotResult& r = h_out[t];
-        if (r.status == STATUS_OVERFLOW) { overflow->push_back(first + t); continue; }     // K1R ring too small: rerun on K2
         if (r.status == STATUS_HAS_N) { rerun_n->push_back(first + t); continue; }         // raw mode: rerun with matrix lookup
         if (r.status == STATUS_BAD_CODE) {
             set_error(ctx, "task " + std::to_string(first + t) + ": invalid (base code > 4)");
@@ -718,7 +713,6 @@ int slot_collect(bsw_ctx* ctx, Slot& s, bsw_result* out, uint32_t* cells, LocalS
         if (cells) cells[first + t] = (uint32_t)r.cells;
     }
     st->tasks += s.count; st->cells += cell_sum; st->kernel_ms += ms;
-    (void)overflow;
     if (bad) { set_error(ctx, "a kernel reported a non-OK task status"); return BSW_ECUDA; }
     return 0;
 }
@@ -786,14 +780,13 @@ struct CallLease {
 // multi-GPU context balances dynamically -- the GPU analogue of task_parse handing the next task to the first PE
 // with room (sw_pe_array_task_parse.v:1600-1650).  No collective: results land in out[task].
 int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out,
-                          uint32_t* cells, int force_kernel, std::vector<size_t>* overflow_out, std::vector<size_t>* rerun_n_out = nullptr)
+                          uint32_t* cells, std::vector<size_t>* rerun_n_out = nullptr)
 {
     const double w0 = now_ms();
     DevParams dp; int sym = 0, max_mat = 0; bool fast_ok = false;
     int rc = make_dev_params(ctx, params, &dp, &sym, &fast_ok, &max_mat);
     if (rc) return rc;
     SchedOptions opt = ctx->opt;
-    if (force_kernel >= 0) opt.force_kernel = force_kernel;                              // the overflow rerun: plain K2
     opt.fast_matrix = fast_ok;
     if (opt.host_threads <= 0) opt.host_threads = default_host_threads();
 
@@ -867,12 +860,12 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
     std::atomic<int> first_err(0);
     std::mutex stat_mu;
     LocalStats total;
-    std::vector<size_t> overflow_all, rerun_all;
+    std::vector<size_t> rerun_all;
 
     auto worker_main = [&](size_t k) {
         Worker& W = *cs.workers[k];
         LocalStats st;
-        std::vector<size_t> ovf, rrn;
+        std::vector<size_t> rrn;
         int r = 0;
         if (cudaSetDevice(ctx->devs[(size_t)W.dev].id) != cudaSuccess) { r = BSW_ECUDA; set_error(ctx, "cudaSetDevice failed"); }
         if (!r && W.slots.size() < (size_t)ctx->slots_per_worker) {
@@ -892,7 +885,7 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
             Slot& s = W.slots[cur];
             cur = (cur + 1) % nslot;
             const double c0 = T();
-            if ((r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn))) break;
+            if ((r = slot_collect(ctx, s, out, cells, &st, &rrn))) break;
             if (trace) tr += "w" + std::to_string(k) + " chunk " + std::to_string(first) + "+" + std::to_string(count) + " collect_prev " + std::to_string(c0) + ".." + std::to_string(T());
             if (lean_mode) {
                 const bool packed2 = lean_mode == 2;
@@ -920,12 +913,11 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
         for (size_t q = 0; q < W.slots.size(); ++q) {                                    // oldest chunk first
             Slot& s = W.slots[(cur + q) % W.slots.size()];
             if (r) { if (s.stream) cudaStreamSynchronize(s.stream); s.busy = false; }    // leave the device quiescent
-            else r = slot_collect(ctx, s, out, cells, &st, &ovf, &rrn);
+            else r = slot_collect(ctx, s, out, cells, &st, &rrn);
         }
         if (r) { int expect = 0; first_err.compare_exchange_strong(expect, r); }
         if (trace) { tr += " done " + std::to_string(T()) + "\n"; fputs(tr.c_str(), stderr); }
         std::lock_guard<std::mutex> g(stat_mu);
-        overflow_all.insert(overflow_all.end(), ovf.begin(), ovf.end());
         rerun_all.insert(rerun_all.end(), rrn.begin(), rrn.end());
         total.pack_ms += st.pack_ms; total.validate_ms += st.validate_ms; total.kernel_ms += st.kernel_ms;
         total.h2d += st.h2d; total.d2h += st.d2h; total.launches += st.launches; total.tasks += st.tasks; total.cells += st.cells;
@@ -948,15 +940,14 @@ int run_extensions_locked(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params
         S.h2d_bytes += total.h2d; S.d2h_bytes += total.d2h; S.kernel_ms += total.kernel_ms;
         S.pack_ms += (total.pack_ms + total.validate_ms) / (double)nworkers;     // average per worker = wall share
         S.wall_ms += now_ms() - w0;
-        S.tasks -= overflow_all.size() + rerun_all.size();          // counted again by the reruns
+        S.tasks -= rerun_all.size();                                // counted again by the rerun
     }
-    if (overflow_out) overflow_out->swap(overflow_all);
     if (rerun_n_out) rerun_n_out->swap(rerun_all);
     if (first_err.load()) adopt_worker_error(ctx);
     return first_err.load();
 }
 
-// Gathers a subset of a task source (the K1R overflow list).
+// Gathers a subset of a task source (a rerun list).
 struct SubsetSrc { const TaskSource* base; const size_t* idx; };
 void fill_subset(const void* self, size_t first, size_t count, ExtTask* out)
 {
@@ -1053,26 +1044,20 @@ int run_wide(bsw_ctx* ctx, const bsw_params* params, const TaskSource& src, cons
     return BSW_OK;
 }
 
-// One pass over a source plus its reruns: K1R tasks whose live window outgrew the ring are rerun on K2, raw-mode tasks
-// that hold an N on the staged path (which classifies them for the matrix-lookup kernel): whole tasks, from scratch,
-// results scattered over the first pass
+// One pass over a source plus its rerun: raw-mode tasks that hold an N go through the staged path (which classifies them
+// for the matrix-lookup kernel) -- whole tasks, from scratch, results scattered over the first pass
 int run_with_reruns(bsw_ctx* ctx, bsw_ctx::CallState& cs, const bsw_params* params, const TaskSource& src, size_t n, bsw_result* out, uint32_t* cells)
 {
-    std::vector<size_t> overflow, rerun_n;
-    int rc = run_extensions_locked(ctx, cs, params, src, n, out, cells, -1, &overflow, &rerun_n);
+    std::vector<size_t> rerun_n;
+    int rc = run_extensions_locked(ctx, cs, params, src, n, out, cells, &rerun_n);
+    if (rc || rerun_n.empty()) return rc;
+    std::sort(rerun_n.begin(), rerun_n.end());
+    const SubsetSrc sub{ &src, rerun_n.data() };
+    std::vector<bsw_result> r2(rerun_n.size());
+    std::vector<uint32_t> c2(cells ? rerun_n.size() : 0);
+    rc = run_extensions_locked(ctx, cs, params, TaskSource{ &sub, fill_subset }, rerun_n.size(), r2.data(), cells ? c2.data() : nullptr, nullptr);
     if (rc) return rc;
-    for (int pass = 0; pass < 2; ++pass) {
-        std::vector<size_t>& list = pass ? rerun_n : overflow;
-        if (list.empty()) continue;
-        std::sort(list.begin(), list.end());
-        const SubsetSrc sub{ &src, list.data() };
-        std::vector<bsw_result> r2(list.size());
-        std::vector<uint32_t> c2(cells ? list.size() : 0);
-        rc = run_extensions_locked(ctx, cs, params, TaskSource{ &sub, fill_subset }, list.size(), r2.data(), cells ? c2.data() : nullptr,
-                                   pass ? -1 : 2, nullptr);
-        if (rc) return rc;
-        for (size_t k = 0; k < list.size(); ++k) { out[list[k]] = r2[k]; if (cells) cells[list[k]] = c2[k]; }
-    }
+    for (size_t k = 0; k < rerun_n.size(); ++k) { out[rerun_n[k]] = r2[k]; if (cells) cells[rerun_n[k]] = c2[k]; }
     return BSW_OK;
 }
 
@@ -1260,7 +1245,6 @@ int bsw_set_option(bsw_ctx* ctx, const char* key, int64_t value)
     else if (k == "chunk_tasks") { if (value < 32) return BSW_EINVAL; ctx->chunk_tasks = (size_t)value; }
     else if (k == "force_kernel") { if (value < 0 || value > 2) return BSW_EINVAL; ctx->opt.force_kernel = (int)value; }
     else if (k == "k2_warps") { if (value != 1 && value != 4) return BSW_EINVAL; ctx->k2_warps = (int)value; }
-    else if (k == "ring") { ctx->opt.ring = value != 0; }
     else if (k == "fused_l2") { ctx->fused_l2 = value != 0; }
     else if (k == "device_plan") { ctx->device_plan = value != 0; }
     else if (k == "k2_narrow") { ctx->k2_narrow = value != 0; }
@@ -1910,21 +1894,15 @@ int bsw_resident_fetch(bsw_ctx* ctx, bsw_resident* R, bsw_result* out, uint32_t*
     const Plan& P = s.plan;
     CUDA_TRY(ctx, cudaMemcpyAsync(s.h_out, s.d_out, P.slots.size() * sizeof(SlotResult), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(s.stream));
-    size_t novf = 0;
     for (size_t k = 0; k < P.slots.size(); ++k) {
         const int64_t t = P.slot_task[k];
         if (t < 0) continue;
         const SlotResult& r = s.h_out[k];
-        if (r.status == STATUS_OVERFLOW) ++novf;
         bsw_result& o = out[(size_t)t];
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
         if (cells) cells[(size_t)t] = (uint32_t)r.cells;
     }
     cudaSetDevice(prev);
-    if (novf) {     // a resident batch is measurement-only and has no rerun stage
-        set_error(ctx, std::to_string(novf) + " tasks outgrew K1R's ring; use the batch call (it reruns them on K2) or set option ring=0");
-        return BSW_ERANGE;
-    }
     return BSW_OK;
 }
 

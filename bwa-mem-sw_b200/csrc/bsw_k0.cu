@@ -32,24 +32,6 @@ __device__ __forceinline__ void k0_copy_block(const uint4* __restrict__ src16, i
     }
 }
 
-// K1R tiles: the query block is written as match planes (per 32 columns four words = the positions of A, C, G, T, then one
-// all-zero block), the form the branch-free cell consumes; long tasks cannot re-code their query in shared memory.
-__device__ __forceinline__ void k0_copy_planes(const uint4* __restrict__ src16, int own_words, int qlen, uint32_t* __restrict__ dst,
-                                               int tile_words, int lane)
-{
-    for (int m = 0; m * 4 < tile_words; ++m) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (m * 4 < own_words) v = __ldg(src16 + m);
-        uint32_t* d = dst + (size_t)(m * 4) * TILE_LANES + lane;
-#pragma unroll
-        for (uint32_t b = 0; b < 4; ++b) {
-            uint32_t pl = k1_eq8(v.x, b) | (k1_eq8(v.y, b) << 8) | (k1_eq8(v.z, b) << 16) | (k1_eq8(v.w, b) << 24);
-            if (32 * m >= qlen) pl = 0;
-            d[b * TILE_LANES] = pl;
-        }
-    }
-}
-
 // Raw mode: the lane's sequence is `len` bytes (one base code each) at an arbitrary byte address.  Eight bases per step:
 // one aligned 8-byte load (the previous one supplies the low part), nibble pack, and two SWAR tests -- any byte above 4,
 // any byte equal to 4.  Reads run at most 15 bytes past the sequence (the raw buffers carry that slack).
@@ -131,8 +113,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_gather_kernel(const __grid_c
         return;
     }
     const uint4* src16 = reinterpret_cast<const uint4*>(A.src);
-    if (hd.nqw_ntw & TILE_ONEHOT) k0_copy_planes(src16 + ss.qoff16, own_q, sp.qlen, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
-    else k0_copy_block(src16 + ss.qoff16, own_q, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
+    k0_copy_block(src16 + ss.qoff16, own_q, A.dst + (size_t)hd.qoff16 * 4, nqw, lane);
     k0_copy_block(src16 + ss.toff16, own_t, A.dst + (size_t)hd.toff16 * 4, ntw, lane);
 }
 

@@ -92,55 +92,6 @@ __global__ void __launch_bounds__(K1_NT) k1_extend_kernel(const __grid_constant_
     }
 }
 
-// K1R: the same lane function for long tasks.  The row buffer is a ring of K1R_RING columns in shared memory (the live
-// window of a row, not the whole query), the match planes / query nibbles are read straight from the tiled arena
-// (coalesced across the lanes of a tile, L1-resident while the lanes advance together).
-template <int GENERIC, int SYM>
-__global__ void __launch_bounds__(K1_NT) k1r_extend_kernel(const __grid_constant__ LaunchArgs A)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
-    const TileHdr hd = A.tiles[blockIdx.x];
-    const uint32_t nqw = hd.nqw_ntw & 0x7fffu;
-    uint32_t* eh = reinterpret_cast<uint32_t*>(smem_raw);
-    const uint32_t slot = hd.slot0 + lane;
-    const SlotParam sp = A.slots[slot];
-    unsigned long long my_cells = 0;
-    if (sp.qlen > 0) {
-        uint32_t* qs = const_cast<uint32_t*>(A.arena) + (size_t)hd.qoff16 * 4u + lane;      // read-only in ring mode (prep = false)
-        const uint32_t* tg = A.arena + (size_t)hd.toff16 * 4u + lane;
-        SlotResult r;
-        k1_task<1, GENERIC, SYM, K1R_RING>(A.p, sp.qlen, sp.tlen, sp.h0, sp.w, (int)nqw, eh + lane, qs, tg, r, false);
-        int4* o = reinterpret_cast<int4*>(A.out + (A.out_index ? A.out_index[slot] : slot));
-        o[0] = make_int4(r.score, r.qle, r.tle, r.gtle);
-        o[1] = make_int4(r.gscore, r.max_off, r.cells, r.status);
-        my_cells = (uint32_t)r.cells;
-    }
-    if (A.cells_total) {
-        for (int o = 16; o; o >>= 1) my_cells += __shfl_xor_sync(0xffffffffu, my_cells, o);
-        if (lane == 0 && my_cells) atomicAdd(A.cells_total, my_cells);
-    }
-}
-
-template <int GENERIC, int SYM>
-static cudaError_t k1r_launch_t(const LaunchArgs& a, cudaStream_t st)
-{
-    if (!a.ntiles) return cudaSuccess;
-    const size_t smem = (size_t)K1R_RING * K1_NT * 4u;
-    auto kern = k1r_extend_kernel<GENERIC, SYM>;
-    static std::atomic<unsigned> smem_set{ 0u };          // per instantiation of this launcher
-    cudaError_t err = ensure_max_smem(kern, smem_set);
-    if (err != cudaSuccess) return err;
-    kern<<<a.ntiles, K1_NT, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t k1r_launch(const LaunchArgs& a, int generic, int sym, cudaStream_t st)
-{
-    if (generic) return sym ? k1r_launch_t<1, 1>(a, st) : k1r_launch_t<1, 0>(a, st);
-    return sym ? k1r_launch_t<0, 1>(a, st) : k1r_launch_t<0, 0>(a, st);
-}
-
 size_t k1_smem_bytes(int qmax, int nqw_max)
 {
     return (size_t)K1_HDR_BYTES + ((size_t)(nqw_max + K1_QS_EXTRA) + (size_t)(qmax + 1 + K1_EH_SLACK)) * K1_NT * 4u;

@@ -178,16 +178,11 @@ BSW_HD int k1_lookup(uint32_t nib, uint32_t rlo, uint32_t rhi)
 // One extension.  eh/qs point at this lane's column 0 / word 0 (stride K1_S); tg at this lane's target word 0 in the
 // tiled arena (stride K1_S).  eh must have qlen + 1 + K1_EH_SLACK columns; qs holds the tile's nqw_tile packed query
 // words of this lane and has room for nqw_max + K1_QS_EXTRA words.
-// RING = 0: eh holds every column of the query.  RING = R (power of two): K1R, long tasks -- eh is a ring of R columns
-// indexed by (column & (R-1)); it only has to hold the live window [beg, end] of a row, which the narrowing keeps a few
-// hundred columns wide even for 10 kb reads.  A row whose candidate window does not fit ends the task with
-// STATUS_OVERFLOW (the host reruns it on K2).  In ring mode qs points at read-only global memory (match planes already
-// built by the K0 gather), so prep must be false.
-template <int VARIANT, int GENERIC, int SYM, int RING = 0>
+template <int VARIANT, int GENERIC, int SYM>
 BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const int h0, const int w, const int nqw_tile,
                     uint32_t* eh, uint32_t* qs, const uint32_t* tg, SlotResult& res, const bool prep = true)
 {
-#define BSW_EHA(J) (eh + (RING ? ((J) & (RING - 1)) : (J)) * K1_S)
+#define BSW_EHA(J) (eh + (J) * K1_S)
     constexpr bool ONEHOT = (VARIANT == 1 && GENERIC == 0);     // the branch-free path of the +a/-b scoring
     const int o_del = P.o_del, e_del = P.e_del, e_ins = P.e_ins;
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
@@ -249,8 +244,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
     {
         eh[0] = (uint32_t)h0 << 16;
         int hv = h0 - P.o_ins;
-        const int jinit = RING ? imin(qlen, RING - 1) : qlen;
-        for (int j = 1; j <= jinit; ++j) { hv -= e_ins; eh[j * K1_S] = (uint32_t)imax(hv, 0) << 16; }
+        for (int j = 1; j <= qlen; ++j) { hv -= e_ins; eh[j * K1_S] = (uint32_t)imax(hv, 0) << 16; }
     }
 
     int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;   // sx:889,1009,919,1019,1029,929
@@ -280,11 +274,6 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             const int zend = imin(j0, lim);
             for (int z = stopmin; z < zend; ++z)
                 if ((*BSW_EHA(z) >> 16) == 0) { lim = imin(lim, z); break; }
-        }
-        if (RING && lim - j0 + 2 > RING) {                                       // the live window does not fit the ring
-            res.score = 0; res.qle = 0; res.tle = 0; res.gtle = 0; res.gscore = 0; res.max_off = 0; res.cells = 0;
-            res.status = STATUS_OVERFLOW;
-            return;
         }
         int fc;                                                                  // first column (sx:1796,1795,1880,1835,849)
         if (VARIANT == 1 || j0 == 0) fc = imax(h0 - (o_del + e_del * (i + 1)), 0); else fc = 0;
@@ -366,8 +355,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                 const int qi = j >> 3;
                 x = funnel_r(qs[qi * K1_S], qs[(qi + 1) * K1_S], (j & 7) * 4);
             }
-            if (RING) ehp = BSW_EHA(j);
-            if (VARIANT == 1 && ONEHOT && !RING && nv >= 16) {
+            if (VARIANT == 1 && ONEHOT && nv >= 16) {
                 // two chunks under one head: one funnel shift yields the match bits of 16 columns, the 16 row-buffer
                 // loads are issued together, and the zero test, the loop bookkeeping and the branches are paid once
                 const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
@@ -408,7 +396,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                     continue;
                 }
             }
-            if (VARIANT == 1 && (!RING || (j & (RING - 1)) <= RING - 8)) {      // ring: a chunk that wraps goes cell by cell
+            if (VARIANT == 1) {
                 const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
                 const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
                 int ckey = K1_KEY_NONE;                      // chunk-local key: (h << 16) + k
@@ -464,7 +452,7 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
                     }
                 }
             }
-            if (VARIANT == 2 && !RING && nv >= 8) {
+            if (VARIANT == 2 && nv >= 8) {
                 const uint32_t w0 = ehp[0 * K1_S], w1 = ehp[1 * K1_S], w2 = ehp[2 * K1_S], w3 = ehp[3 * K1_S];
                 const uint32_t w4 = ehp[4 * K1_S], w5 = ehp[5 * K1_S], w6 = ehp[6 * K1_S], w7 = ehp[7 * K1_S];
                 uint32_t zm = min3_u16x2(w0, w1, w2);
@@ -506,7 +494,6 @@ BSW_HD void k1_task(const DevParams& P, const int qlen, const int tlen, const in
             // careful path: cell by cell, with the narrowing events (V1) or the V2 recurrence
             const int kmax = nv < 8 ? nv : 8;
             for (int k = 0; k < kmax; ++k, ++j, ehp += K1_S) {
-                if (RING) ehp = BSW_EHA(j);
                 const uint32_t wd = *ehp;
                 int M = (int)(wd >> 16), e = (int)(wd & 0xffffu);
                 if (VARIANT == 1 && M == 0) {

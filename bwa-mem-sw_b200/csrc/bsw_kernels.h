@@ -39,9 +39,6 @@ size_t dp_bins_per_major();     // u32 counters per non-empty (class, qlen/16) b
 cudaError_t k1_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);
 size_t k1_smem_bytes(int qmax, int nqw_max);
 
-// K1R: K1's lane function over a 512-column ring for long tasks (V1); overflowing tasks come back with STATUS_OVERFLOW.
-cudaError_t k1r_launch(const LaunchArgs& a, int generic, int sym, cudaStream_t st);
-
 // K3: fused seed-task kernel (level 2 on the device): left + right extension, band retry, clip, record.
 // a.tiles = (left, right) tile pairs, a.seeds[pair*32+lane], a.out[pair*32+lane] = bsw_aln_record.
 cudaError_t k3_launch(const LaunchArgs& a, int variant, int generic, int sym, cudaStream_t st);

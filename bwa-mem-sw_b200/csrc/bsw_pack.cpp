@@ -154,8 +154,6 @@ int PACK_TASKS_NAME(const ExtTask* tasks, size_t n, int max_mat, const SchedOpti
             if (top == 4 || !opt.fast_matrix) c |= 1;        // an N: matrix-lookup scoring
             bool longtask = opt.force_kernel == 2 || (opt.force_kernel == 0 && t.qlen >= opt.k2_min_qlen) || t.qlen > k1cap;
             if (longtask) c |= 2;
-            // K1R needs the first row (min(qlen, w+1) columns + end slot) inside the ring
-            if (longtask && opt.ring && opt.variant == 1 && opt.force_kernel != 2 && std::min(t.qlen, t.w + 1) + 2 <= K1R_RING) c |= 4;
         }
         cls[i] = c;
         if (e) {

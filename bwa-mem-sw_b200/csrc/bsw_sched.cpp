@@ -130,7 +130,7 @@ static inline size_t k2_task_smem(int qmax, int wmax)
     const size_t qcap = ((size_t)qmax + 1 + 255) & ~(size_t)255;
     const bool ring = qcap > 2048 && 2 * (size_t)wmax + 513 <= 2048;
     const size_t rcap = ring ? 2048 : qcap;
-    return 128 + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 8) * 4u + 16u;
+    return 128 + ((ring ? 0 : (qcap >> 3)) + 4 + (rcap >> 5) + 4 + rcap + 16) * 4u + 16u;
 }
 static inline int occupancy(size_t smem)
 {
@@ -160,7 +160,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     //   big plans and K2 classes: [class:3][qlen:13][tlen/4:10][h0/2:6] (K2: qlen/8) -- with thousands of tasks per exact
     //       qlen the three-level sort is already 0.99 efficient, and it measured 5 % faster there than the width key
     //       (1 107 vs 1 050 GCUPS on the resident 1 M x 150 bp plan).
-    // classes: 0 K1 fast, 1 K1 matrix, 2 K1R fast, 3 K1R matrix, 4 K2 fast, 5 K2 matrix
+    // classes: 0 K1 fast, 1 K1 matrix, 4 K2 fast, 5 K2 matrix
     std::vector<uint32_t>& key = plan->key; std::vector<uint32_t>& order = plan->order;
     std::vector<uint32_t>& tmp = plan->tmp; std::vector<uint32_t>& hist = plan->hist;
     key.resize(n); order.resize(n); tmp.resize(n);
@@ -169,7 +169,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
         // 22-bit keys (two radix passes): [class:3][qlen/16:7][min(qlen,h0)/4:6][tlen/8:6]; K2 classes [class:3][qlen/128:7][tlen/512:12]
         for (size_t i = 0; i < n; ++i) {
             const ExtTask& t = tasks[i];
-            const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
+            const uint32_t c = ((cls[i] & 2u) ? 4u : 0u) | (cls[i] & 1u);
             if (cls[i] & 2u) {
                 const uint32_t ql = (uint32_t)std::min(t.qlen >> 7, 127), tl = (uint32_t)std::min(t.tlen >> 9, 4095);
                 key[i] = (c << 19) | ((127u - ql) << 12) | (4095u - tl);
@@ -182,7 +182,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
     } else {
         for (size_t i = 0; i < n; ++i) {
             const ExtTask& t = tasks[i];
-            const uint32_t c = ((cls[i] & 2u) ? ((cls[i] & 4u) ? 2u : 4u) : 0u) | (cls[i] & 1u);
+            const uint32_t c = ((cls[i] & 2u) ? 4u : 0u) | (cls[i] & 1u);
             const uint32_t ql = (cls[i] & 2u) ? (uint32_t)std::min(t.qlen >> 3, 8191) : (uint32_t)std::min(t.qlen, 8191);
             const uint32_t tl = (uint32_t)std::min(t.tlen >> 2, 1023), h = (uint32_t)std::min(t.h0 >> 1, 63);
             key[i] = (c << 29) | ((8191u - ql) << 16) | ((1023u - tl) << 6) | (63u - h);
@@ -212,9 +212,8 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
         size_t cend = i;
         while (cend < n && (key[order[cend]] >> class_shift) == c) ++cend;
         const bool is_k2 = c >= 4u;
-        const bool is_ring = (c & 6u) == 2u;
         Launch L{};
-        L.kind = is_k2 ? 2 : (is_ring ? 4 : 1); L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
+        L.kind = is_k2 ? 2 : 1; L.generic = (int)(c & 1u); L.tile0 = (uint32_t)plan->tiles.size();
         int occ0 = 0;
         while (i < cend) {
             // one K2 task or one K1 tile of 32 tasks
@@ -262,10 +261,8 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                         plan->slot_task.push_back(-1);
                     }
                 }
-                int nqw = (tq + 7) >> 3;
+                const int nqw = (tq + 7) >> 3;
                 const int ntw = (tt + 7) >> 3;
-                const bool planes = is_ring && (c & 1u) == 0;                   // K1R fast: K0 writes match planes
-                if (planes) nqw = 4 * (((tq + 31) >> 5) + 1);
                 if (is_k2) {
                     hd[sub].qoff16 = src[order[i]].qoff16;                      // K2 reads the source arena directly
                     hd[sub].toff16 = src[order[i]].toff16;
@@ -274,16 +271,16 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
                     hd[sub].toff16 = (uint32_t)arena16; arena16 += (size_t)ntw * TILE_LANES * 4 / 16;
                     ++plan->n_k1_tiles;
                 }
-                hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16) | (planes ? TILE_ONEHOT : 0u);
+                hd[sub].nqw_ntw = (uint32_t)nqw | ((uint32_t)ntw << 16);
                 qmax = std::max(qmax, tq); nqw_max = std::max(nqw_max, nqw);
             }
-            const size_t smem = is_ring ? (size_t)K1R_RING * TILE_LANES * 4u : is_k2 ? k2_task_smem(qmax, wmax) : k1_tile_smem(qmax, nqw_max);
+            const size_t smem = is_k2 ? k2_task_smem(qmax, wmax) : k1_tile_smem(qmax, nqw_max);
             // bucket boundary: start a new launch when this tile would fit at >= 1.3x the occupancy of the launch
             const int occ = occupancy(smem);
             L.wmax = std::max(L.wmax, wmax);
             if (occ0 == 0) { occ0 = occ; L.qmax = qmax; L.nqw_max = nqw_max; }
             else if (qmax > L.qmax) { L.qmax = qmax; L.nqw_max = std::max(L.nqw_max, nqw_max); }   // saturated sort key (very long tasks)
-            else if (!is_k2 && !is_ring && occ * 100 >= occ0 * bucket_pct) {      // K2 / K1R: one launch per class (measured: bucket tails cost more than occupancy gains)
+            else if (!is_k2 && occ * 100 >= occ0 * bucket_pct) {      // K2: one launch per class (measured: bucket tails cost more than occupancy gains)
                 close_launch(L, (uint32_t)plan->tiles.size());
                 L.tile0 = (uint32_t)plan->tiles.size(); L.qmax = qmax; L.nqw_max = nqw_max; L.wmax = wmax; occ0 = occ;
             }
@@ -297,7 +294,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
 
 bool build_dp_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g)
 {
-    if (n == 0 || opt.ring) return false;
+    if (n == 0) return false;
     DpBuckets bks;
     memset(&bks, 0, sizeof(bks));
     for (size_t i = 0; i < n; ++i) {
@@ -309,9 +306,10 @@ bool build_dp_plan(const ExtTask* tasks, const uint8_t* cls, size_t n, const Sch
 
 bool dp_geometry(const DpBuckets& bks, size_t n, const SchedOptions& opt, Plan* plan, DpGeometry* g)
 {
+    (void)opt;
     plan->tiles.clear(); plan->slots.clear(); plan->slot_src.clear(); plan->slot_task.clear(); plan->launches.clear();
     plan->tiled_words = 0; plan->est_cells = 0; plan->n_k1_tiles = 0;
-    if (n == 0 || opt.ring) return false;
+    if (n == 0) return false;
     const DpBuckets::B (*bk)[128] = bks.bk;
     static const int bucket_env = getenv("BSW_BUCKET_PCT") ? atoi(getenv("BSW_BUCKET_PCT")) : 0;
     const int bucket_pct = bucket_env ? bucket_env : (n >= 400000 ? 115 : (n >= 100000 ? 130 : 200));

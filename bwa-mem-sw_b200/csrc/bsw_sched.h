@@ -31,8 +31,6 @@ struct SchedOptions {
     int k2_min_qlen = 384;      // auto mode: tasks at least this long go to the intra-task kernel
     int host_threads = 0;       // 0 = hardware concurrency (capped)
     bool fast_matrix = true;    // the 5x5 matrix is (+a / -b, N row/col anything): N-free tasks may use FAST scoring
-    bool ring = false;          // long V1 tasks whose first row fits run on K1R (ring row buffer in K1's lane function).
-                                // Off by default: measured slower than K2 (3 warps/SM with a 512-column ring), see DESIGN.md
 };
 
 constexpr int K1_QLEN_CAP = 1536;        // shared-memory limit of one K1 tile (227 KB / (32 lanes * 4.5 B per column))
@@ -43,7 +41,7 @@ constexpr int SCORE_CAP   = 32767;       // 16-bit row state: h0 + qlen*max(mat)
 constexpr int WIDE_QLEN_CAP = 1 << 20, WIDE_TLEN_CAP = 1 << 22, WIDE_SCORE_CAP = 0x3fffffff;
 
 struct Launch {
-    int kind;          // 1 = K1, 2 = K2, 4 = K1R (long tasks, ring row buffer), 5 = K3 (pairs: left tile, right tile)
+    int kind;          // 1 = K1, 2 = K2, 5 = K3 (pairs: left tile, right tile)
     int generic;       // 1 = matrix lookup scoring
     uint32_t tile0, ntiles;
     int qmax, nqw_max;
@@ -69,7 +67,7 @@ struct Plan {
 size_t source_arena_bound(const ExtTask* tasks, size_t n);
 
 // Fused validate + classify + pack (single pass, single thread).  cls: bit0 = needs matrix-lookup scoring (contains N,
-// or the matrix is not +a/-b), bit1 = long task (K2 or K1R), bit2 = long task that may start on K1R.  src[i] = offsets of task i's packed sequences in `arena`.
+// or the matrix is not +a/-b), bit1 = long task (K2).  src[i] = offsets of task i's packed sequences in `arena`.
 // Returns 0 or a negative BSW_E* code; on error *bad_task is the first offending task and msg explains.
 int pack_tasks(const ExtTask* tasks, size_t n, int max_mat, const SchedOptions& opt, uint8_t* cls, SlotSrc* src,
                uint32_t* arena, size_t* words_used, size_t* bad_task, std::string* msg);
@@ -100,7 +98,7 @@ void build_plan(const ExtTask* tasks, const uint8_t* cls, const SlotSrc* src, si
 // follows from per-bucket counts -- the sort key's major field is qlen/16, so class c's tiles are runs of buckets in
 // descending order.  Fills plan->tiles (offsets and slot0; word counts are upper bounds the device replaces),
 // plan->launches, n_k1_tiles, tiled_words.  Returns false when the chunk holds a task the device planner does not take
-// (long tasks: K2 / K1R classes), in which case build_plan must be used.
+// (long tasks: the K2 classes), in which case build_plan must be used.
 struct DpGeometry {
     uint32_t class_count[2], class_pos0[2], class_slot0[2], class_tile0[2]; uint32_t ntiles; size_t nslots;
     uint32_t nmajor, major_start[192]; uint8_t major_of[256];      // non-empty (class, qlen/16) buckets in sorted order

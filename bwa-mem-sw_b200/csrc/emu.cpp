@@ -38,20 +38,6 @@ void run_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, co
     }
 }
 
-template <int GENERIC, int SYM>
-void run_ring_tile(const DevParams& dp, const TileHdr& hd, const SlotParam* slots, uint32_t* arena, SlotResult* out)
-{
-    const int nqw = (int)(hd.nqw_ntw & 0x7fffu);
-    std::vector<uint32_t> eh((size_t)K1R_RING * K1_S, 0xdeadbeefu);
-    for (int lane = 0; lane < K1_S; ++lane) {
-        const SlotParam& sp = slots[hd.slot0 + lane];
-        if (sp.qlen <= 0) continue;
-        k1_task<1, GENERIC, SYM, K1R_RING>(dp, sp.qlen, sp.tlen, sp.h0, sp.w, nqw, eh.data() + lane,
-                                           arena + (size_t)hd.qoff16 * 4 + lane, arena + (size_t)hd.toff16 * 4 + lane,
-                                           out[hd.slot0 + lane], false);
-    }
-}
-
 // Host restatement of the k0 gather kernel (bsw_k0.cu): lane l of a K1 tile copies its task's packed words from the
 // task-major source arena into the tile-interleaved block.
 void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
@@ -63,17 +49,6 @@ void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
             const SlotParam& sp = P.slots[hd.slot0 + lane];
             const SlotSrc& ss = P.slot_src[hd.slot0 + lane];
             const int own_q = sp.qlen > 0 ? ((sp.qlen + 31) >> 5) * 4 : 0, own_t = sp.tlen > 0 ? ((sp.tlen + 31) >> 5) * 4 : 0;
-            if (hd.nqw_ntw & TILE_ONEHOT) {
-                for (int m = 0; m * 4 < nqw; ++m) {
-                    uint32_t v[4];
-                    for (int u = 0; u < 4; ++u) v[u] = (4 * m + u < own_q) ? src[(size_t)ss.qoff16 * 4 + 4 * m + u] : 0u;
-                    for (uint32_t b = 0; b < 4; ++b) {
-                        uint32_t pl = k1_eq8(v[0], b) | (k1_eq8(v[1], b) << 8) | (k1_eq8(v[2], b) << 16) | (k1_eq8(v[3], b) << 24);
-                        if (32 * m >= sp.qlen) pl = 0;
-                        dst[(size_t)hd.qoff16 * 4 + (size_t)(4 * m + (int)b) * TILE_LANES + lane] = pl;
-                    }
-                }
-            } else
             for (int k = 0; k < nqw; ++k) dst[(size_t)hd.qoff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_q ? src[(size_t)ss.qoff16 * 4 + k] : 0u;
             for (int k = 0; k < ntw; ++k) dst[(size_t)hd.toff16 * 4 + (size_t)k * TILE_LANES + lane] = k < own_t ? src[(size_t)ss.toff16 * 4 + k] : 0u;
         }
@@ -85,9 +60,8 @@ void gather_host(const Plan& P, const uint32_t* src, uint32_t* dst)
 extern "C" {
 
 // info[0] = launches, info[1] = tiles, info[2] = arena words, info[3] = padded lanes
-int bsw_emu_force_kernel = 1;   // 1: everything on K1; 0: auto (long tasks -> K1R; tasks that need K2 make the call fail)
+int bsw_emu_force_kernel = 1;   // 1: everything on K1; 0: auto (tasks that need K2 make the call fail)
 int bsw_emu_k2_min_qlen = 384;
-int bsw_emu_ring = 0;           // 1: long tasks go to K1R (the ring-buffer lane function)
 
 int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8_t* qbuf, const int64_t* qoff,
                               const uint8_t* tbuf, const int64_t* toff, const int32_t* h0, const int32_t* w, size_t n,
@@ -114,7 +88,7 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
 
     SchedOptions opt;
     opt.variant = variant; opt.force_kernel = bsw_emu_force_kernel; opt.fast_matrix = fast; opt.host_threads = 4;
-    opt.k2_min_qlen = bsw_emu_k2_min_qlen; opt.ring = bsw_emu_ring != 0;
+    opt.k2_min_qlen = bsw_emu_k2_min_qlen;
     std::vector<ExtTask> v(n);
     for (size_t i = 0; i < n; ++i) {
         ExtTask& x = v[i];
@@ -136,13 +110,6 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
     gather_host(P, src.data(), arena.data());
     std::vector<SlotResult> res(P.slots.size());
     for (const Launch& L : P.launches) {
-        if (L.kind == 4) {
-            for (uint32_t t = L.tile0; t < L.tile0 + L.ntiles; ++t) {
-                if (L.generic) { if (sym) run_ring_tile<1, 1>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); else run_ring_tile<1, 0>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); }
-                else           { if (sym) run_ring_tile<0, 1>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); else run_ring_tile<0, 0>(dp, P.tiles[t], P.slots.data(), arena.data(), res.data()); }
-            }
-            continue;
-        }
         if (L.kind != 1) return BSW_ERANGE;
         for (uint32_t t = L.tile0; t < L.tile0 + L.ntiles; ++t) {
             const TileHdr& hd = P.tiles[t];
@@ -157,7 +124,6 @@ int bsw_emu_extend_batch_flat(const bsw_params* params, int variant, const uint8
         const int64_t t = P.slot_task[k];
         if (t < 0) { ++pad; continue; }
         const SlotResult& r = res[k];
-        if (r.status == STATUS_OVERFLOW) { if (cells) cells[t] = 0xffffffffu; bsw_result& z = out[t]; z.score = z.qle = z.tle = z.gtle = z.gscore = z.max_off = -999; continue; }
         bsw_result& o = out[t];
         o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
         if (cells) cells[t] = (uint32_t)r.cells;

@@ -64,8 +64,7 @@ const char *bsw_version(void);
  * "device_plan" {1,0} sort + tile building on the device / on the host; "k2_narrow" {1,0} register path for narrow K2 rows;
  * "wide" {1,0,2} tasks outside the 16-bit envelope of K1 / K2 (h0 + qlen*max(mat) > 32767, qlen > 40000 or tlen > 500000): 1 = the
  * batch is split and they run on the 32-bit kernel K5 (default), 0 = the batch is refused with BSW_ERANGE, 2 = every task on K5;
- * "fpga_strict" {0,1} bsw_fpga_batch refuses tasks outside the FPGA's 8-bit envelope; "ring" {0,1} experimental K1 ring kernel
- * for long tasks (measured slower than K2, off);
+ * "fpga_strict" {0,1} bsw_fpga_batch refuses tasks outside the FPGA's 8-bit envelope;
  * "kernel_timing" {0,1} record CUDA events around each chunk's kernels for bsw_stats.kernel_ms (default 0:
  *                       the batch calls then leave kernel_ms at 0; bsw_resident_run always times its launches) */
 int  bsw_set_option(bsw_ctx *ctx, const char *key, int64_t value);

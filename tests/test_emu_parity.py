@@ -90,38 +90,10 @@ def _emu_flags(B, **kw):
     return {k: C.c_int.in_dll(B.emu_lib(), "bsw_emu_" + k) for k in kw}
 
 
-def test_ring_row_buffer_lane_function(B, O):
-    """K1R = k1_task over a 512-column ring + match planes built by the gather (long tasks).  Auto kernel selection with
-    a low K2 threshold sends every task of at least 64 bases through it; 1-10 kb reads at w=500 as well."""
-    flags = _emu_flags(B, force_kernel=0, k2_min_qlen=0, ring=0)
-    flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 0, 64, 1
-    try:
-        info = run_both(B, O, B.synth_tasks("cfg3_mixed", 3000, seed=21))
-        assert info[0] >= 2                                         # K1 and K1R launches
-        run_both(B, O, B.synth_tasks("cfg3_mixed", 1500, seed=22, n_frac=0.02), o_del=4, e_del=2, o_ins=7, e_ins=1)
-        run_both(B, O, B.synth_tasks("cfg4_long", 6, seed=23))
-    finally:
-        flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 1, 384, 0
-
-
-def test_ring_overflow_is_reported(B, O):
-    """A window wider than the ring must come back as an overflow (the product reruns such tasks on K2), never as a wrong answer."""
-    flags = _emu_flags(B, force_kernel=0, k2_min_qlen=0, ring=0)
-    flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 0, 64, 1
-    try:
-        rng = np.random.default_rng(5)
-        q = rng.integers(0, 4, 3000).astype(np.uint8)              # perfect 3 kb match, h0 = 400, w = 400: the window grows past 510
-        qbuf, qoff, tbuf, toff = flat_from_lists([q], [np.concatenate([q, q[:200]])])
-        res, cells, _ = B.emu_extend_batch(B.make_params(), qbuf, qoff, tbuf, toff, [400], [400])
-        assert cells[0] == 0xffffffff and res["score"][0] == -999
-    finally:
-        flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 1, 384, 0
-
-
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_randomised_small_tasks(B, O, seed):
     """Thousands of adversarial little tasks (h0 down to 1, w down to 0, ties, indels) under random scoring, both variants,
-    through the K1 and K1R lane functions."""
+    through the K1 lane function."""
     from helpers import random_small_tasks
     rng = np.random.default_rng(1000 + seed)
     t = random_small_tasks(rng, 3000)
@@ -130,9 +102,3 @@ def test_randomised_small_tasks(B, O, seed):
     for pk in pks:
         for variant in (1, 2):
             run_both(B, O, t, variant=variant, **pk)
-        flags = _emu_flags(B, force_kernel=0, k2_min_qlen=0, ring=0)
-        flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 0, 8, 1
-        try:
-            run_both(B, O, t, **pk)
-        finally:
-            flags["force_kernel"].value, flags["k2_min_qlen"].value, flags["ring"].value = 1, 384, 0

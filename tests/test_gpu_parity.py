@@ -499,13 +499,22 @@ def test_level2_seeds_beyond_16_bits(B, O, ctx):
     assert int(want["score"].max()) > 60_000
 
 
-def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
-    """Option ring=1: long tasks run on K1R (ring row buffer); a task whose window outgrows the ring is rerun on K2."""
-    ctx.set_option("ring", 1)
-    try:
-        _k1r_cases(B, O, ctx)
-    finally:
-        ctx.set_option("ring", 0)
+def test_long_and_wide_rows_on_k2(B, O, ctx):
+    """K2 on a mix that crosses its thresholds (k2_min_qlen = 64), other gap penalties with N bases, near-perfect 3 kb
+    matches whose windows grow to the band (one and four warps, with and without the narrow-row path)."""
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 20_000, seed=80), opts={"k2_min_qlen": 64})
+    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=81, n_frac=0.02), opts={"k2_min_qlen": 64}, o_del=4, e_del=2, o_ins=7, e_ins=1)
+    rng = np.random.default_rng(5)
+    qs, ts, h0, w = [], [], [], []
+    for k in range(40):                                       # near-perfect 3 kb matches with a big h0: windows beyond 510 columns
+        q = rng.integers(0, 4, 3000).astype(np.uint8)
+        t = np.concatenate([q, q[:200]]).astype(np.uint8)
+        t[rng.random(len(t)) < 0.01] = 0
+        qs.append(q); ts.append(t); h0.append(400 if k % 2 == 0 else 30); w.append(400)
+    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
+    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
+    both(B, O, ctx, t)
+    both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=84))
     both(B, O, ctx, B.synth_tasks("cfg4_long", 32, seed=82))          # default: K2 (one warp per task, ring row buffer)
     both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=83), opts={"k2_warps": 4})
     ctx.set_option("k2_warps", 1)
@@ -520,25 +529,9 @@ def test_k1r_ring_kernel_and_overflow_rerun(B, O, ctx):
     both(B, O, ctx, wide, opts={"k2_narrow": 0}); ctx.set_option("k2_narrow", 1)
 
 
-def _k1r_cases(B, O, ctx):
-    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 20_000, seed=80), opts={"k2_min_qlen": 64})       # K1 + K1R mix
-    both(B, O, ctx, B.synth_tasks("cfg3_mixed", 5_000, seed=81, n_frac=0.02), opts={"k2_min_qlen": 64}, o_del=4, e_del=2, o_ins=7, e_ins=1)
-    rng = np.random.default_rng(5)
-    qs, ts, h0, w = [], [], [], []
-    for k in range(40):                                       # near-perfect 3 kb matches with a big h0: windows grow past 510 columns
-        q = rng.integers(0, 4, 3000).astype(np.uint8)
-        t = np.concatenate([q, q[:200]]).astype(np.uint8)
-        t[rng.random(len(t)) < 0.01] = 0
-        qs.append(q); ts.append(t); h0.append(400 if k % 2 == 0 else 30); w.append(400)
-    qbuf, qoff, tbuf, toff = flat_from_lists(qs, ts)
-    t = dict(qbuf=qbuf, qoff=qoff, tbuf=tbuf, toff=toff, h0=np.array(h0, np.int32), w=np.array(w, np.int32))
-    both(B, O, ctx, t)
-    both(B, O, ctx, B.synth_tasks("cfg4_long", 16, seed=84))
-
-
 @pytest.mark.parametrize("seed", [1, 2])
 def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
-    """Adversarial little tasks (h0 down to 1, w down to 0, ties, indels), random scoring, through K1, K1R, K2 (1 and 4
+    """Adversarial little tasks (h0 down to 1, w down to 0, ties, indels), random scoring, through K1, K2 (1 and 4
     warps, both variants, with and without the narrow-row path) and the fused level 2."""
     from helpers import random_small_tasks
     rng = np.random.default_rng(2000 + seed)
@@ -548,7 +541,7 @@ def test_randomised_small_tasks_every_kernel(B, O, ctx, seed):
     for p in (dict(), pk):
         both(B, O, ctx, t, **p)
         both(B, O, ctx, t, variant=2, **p)
-        both(B, O, ctx, t, opts={"ring": 1, "k2_min_qlen": 8}, **p); ctx.set_option("ring", 0)
+        both(B, O, ctx, t, opts={"k2_min_qlen": 8}, **p)
         both(B, O, ctx, t, opts={"force_kernel": 2}, **p)
         both(B, O, ctx, t, opts={"force_kernel": 2, "k2_warps": 4}, **p); ctx.set_option("k2_warps", 1)
         both(B, O, ctx, t, opts={"force_kernel": 2, "k2_narrow": 0}, **p); ctx.set_option("k2_narrow", 1)

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bsw_b200 as B
 ctx = B.Context(); p = B.make_params()
-for k in ("ring", "k2_narrow", "k2_warps", "k2_min_qlen"):
+for k in ("k2_narrow", "k2_warps", "k2_min_qlen"):
     if os.environ.get(k.upper()): ctx.set_option(k, int(os.environ[k.upper()]))
 t = B.synth_tasks("cfg4_long", 20000)
 flat = (t["qbuf"], t["qoff"], t["tbuf"], t["toff"], t["h0"], t["w"])

@@ -24,14 +24,14 @@ def check(name, n, variant=1, n_frac=0.0, **opts):
     print(name, n, variant, n_frac, opts, "OK" if ok else "MISMATCH", flush=True)
     bad += 0 if ok else 1
     for k in opts:
-        ctx.set_option(k, {"force_kernel": 0, "ring": 0, "k2_narrow": 1, "k2_warps": 1, "k2_min_qlen": 384}[k])
+        ctx.set_option(k, {"force_kernel": 0, "k2_narrow": 1, "k2_warps": 1, "k2_min_qlen": 384}[k])
     ctx.set_option("variant", 1)
 
 
 check("cfg3_mixed", 1500)
 check("cfg3_mixed", 1500, n_frac=0.02)
 check("cfg3_mixed", 1500, variant=2)
-check("cfg3_mixed", 1500, ring=1, k2_min_qlen=64)
+check("cfg3_mixed", 1500, k2_min_qlen=64)
 check("cfg3_mixed", 600, force_kernel=2)
 check("cfg3_mixed", 600, force_kernel=2, k2_warps=4)
 check("cfg3_mixed", 600, variant=2, force_kernel=2)
