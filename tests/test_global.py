@@ -10,14 +10,16 @@ import pytest
 MINF = -(1 << 29)
 
 
-def gotoh(q, t, mat, o_ins, e_ins, o_del, e_del):
+def gotoh(q, t, mat, o_ins, e_ins, o_del, e_del, w=None):
+    """Three-matrix global alignment, written from the textbook recurrence; w: only cells with |i - j| <= w exist."""
     n, m = len(q), len(t)
+    if w is None: w = n + m
     H = np.full((m + 1, n + 1), MINF, dtype=np.int64); E = H.copy(); F = H.copy()
     H[0, 0] = 0
-    for j in range(1, n + 1): H[0, j] = -(o_ins + e_ins * j)
-    for i in range(1, m + 1): H[i, 0] = -(o_del + e_del * i)
+    for j in range(1, min(n, w) + 1): H[0, j] = -(o_ins + e_ins * j)
+    for i in range(1, min(m, w) + 1): H[i, 0] = -(o_del + e_del * i)
     for i in range(1, m + 1):
-        for j in range(1, n + 1):
+        for j in range(max(1, i - w), min(n, i + w) + 1):
             E[i, j] = max(E[i - 1, j] - e_del, H[i - 1, j] - o_del - e_del)      # gap in the query (deletion)
             F[i, j] = max(F[i, j - 1] - e_ins, H[i, j - 1] - o_ins - e_ins)      # gap in the target (insertion)
             H[i, j] = max(H[i - 1, j - 1] + mat[t[i - 1] * 5 + q[j - 1]], E[i, j], F[i, j])
@@ -79,6 +81,20 @@ def test_full_band_equals_gotoh(O):
     for q, t in cases(12, 120, 1, 40):
         score, _ = O.global_align(p, q, t, len(q) + len(t))
         assert score == gotoh(q, t, mat, p.o_ins, p.e_ins, p.o_del, p.e_del)
+
+
+def test_banded_score_equals_banded_gotoh(O):
+    """The band of ksw_global2 is |i - j| <= w on the (target row, query column) grid: an independent banded Gotoh gives
+    the same optimum for every band that can reach the last cell."""
+    p = O.make_params(o_del=5, e_del=2, o_ins=7, e_ins=1)
+    mat = np.frombuffer(bytes(p.mat), dtype=np.int8)
+    rng = np.random.default_rng(13)
+    for q, t in cases(13, 150, 1, 50):
+        w = abs(len(q) - len(t)) + int(rng.integers(0, 6))
+        score, cig = O.global_align(p, q, t, w)
+        assert score == gotoh(q, t, mat, p.o_ins, p.e_ins, p.o_del, p.e_del, w)
+        s, qc, tc = rescore(cig, q, t, mat, p.o_ins, p.e_ins, p.o_del, p.e_del)
+        assert (s, qc, tc) == (score, len(q), len(t))
 
 
 def test_max_cigar_overflow_is_reported(O):
