@@ -257,7 +257,10 @@ __device__ __forceinline__ void k2_round_packed(uint32_t* eh, const uint32_t* __
         const uint32_t f = max_s16x2(fl[k], upk + (uint32_t)k * C.c_ne_ins);
         hq[k] = max_s16x2(hh[k], f);                                               // {h, 0}  sx:1809
         if (VARIANT == 1) t[k] = add_max_s16x2(hq[k], C.c_noe_del, C.zero);        // sx:1866,1862
-        lkey = add_max((int)hq[k], k, lkey);                                       // sx:1808,1816: (h << 16) + k, ties to the right
+        // sx:1808,1816: (h << 16) + k, ties to the right.  A zeroed column left of j0 yields h = 0 with +a/-b scoring and
+        // under V2's zero guard, but max(s, 0) with a looked-up score under V1: there it is kept out of the arg-max
+        // (it could win a row whose live cells are all below max(mat), e.g. the all-zero row that ends a task)
+        if (!(GENERIC && VARIANT == 1) || k >= lo) lkey = add_max((int)hq[k], k, lkey);
         if (VARIANT == 1) nzacc += min(hq[k], 1u) << k;
     }
     // arg-max over ALL the lane's columns: a column right of the window can only win in the lane that holds `lim`; the
