@@ -613,7 +613,8 @@ __global__ void __launch_bounds__(32 * K2_WARPS, K2_WARPS == 1 ? 24 : 1) k2_exte
         if (HI && (key & 0xffff) >= lim) {
             // the packed round takes the arg-max over all the columns of a lane; the lane that holds `lim` also holds columns
             // right of the window, and one of them won: redo the last round's share with those columns left out, from the
-            // row buffer (slot c + 1 holds h of column c).  Rare.
+            // row buffer (slot c + 1 holds h of column c).  Taken by 5-15 % of the rows (stale H values right of a window
+            // that has just moved left are often larger than anything in it); ~40 instructions when it is.
             int mk2 = keyprev;
             for (int k = 0; k < cpl_last; ++k) {
                 const int c = jl_last + k;
