@@ -12,8 +12,9 @@ intra-task kernel for long reads.  Lane-parallel numpy, the same packed 16x2 wor
   * the 2 048-column ring of long queries (12-column lanes may straddle its end).
 
 Compared with the scalar oracle on every field and the cell count -- so the ALGORITHM is covered by the CPU suite; the
-kernel itself is compared with the oracle on the GPU (tests/test_gpu_parity.py).  The register path for rows below 64
-columns (k2_narrow_row) is a scalar-cell variant and is not modelled: such rows take the 8-column round here."""
+kernel itself is compared with the oracle on the GPU (tests/test_gpu_parity.py).  Every V1 task runs twice: all rows on
+the packed round (option k2_narrow = 0), and rows below 64 columns on the registers-only path (k2_narrow_row: one or two
+columns per lane from j0, scalar cell, live masks) as the kernel does by default."""
 import ctypes as C
 
 import numpy as np
@@ -46,7 +47,7 @@ def max2(a, b):
     return pack(np.maximum(hi16(a), hi16(b)), np.maximum(lo16(a), lo16(b)))
 
 
-def k2_model(p, query, target, h0, w, variant):
+def k2_model(p, query, target, h0, w, variant, narrow=False):
     mat25 = np.frombuffer(bytes(p.mat), dtype=np.int8).astype(np.int64)
     a, b = int(mat25[0]), -int(mat25[1])
     generic = bool((np.asarray(query) == 4).any() or (np.asarray(target) == 4).any()) or any(
@@ -143,6 +144,49 @@ def k2_model(p, query, target, h0, w, variant):
                     zb[(jl[l] + K) & rm] = (ow[l] != 0).astype(np.int64)
         return carry, hcarry, key, (zbits, jl, cpl)
 
+    def narrow_row(cpl, j0, lim, fc, tb):
+        """k2_narrow_row: one round, lane l owns the cpl columns j0 + cpl*l + k (no alignment), scalar cell, live masks."""
+        K = np.arange(cpl, dtype=np.int64)
+        c0 = j0 + cpl * L32
+        col = c0[:, None] + K[None, :]
+        live = col < lim
+        wd = np.where(live, eh[np.minimum(col & rm, len(eh) - 1)], 0)
+        nib = q[np.minimum(col, qlen + 63)]
+        sc = mat25[5 * tb + np.minimum(nib, 4)] if generic else np.where(nib == tb, a, -b)
+        sc = np.where(live | generic, sc, np.where(0 == tb, a, -b))          # dead columns read a zero query word
+        M, e = wd >> 16, wd & 0xffff
+        hh = np.maximum(M + sc, e)
+        g = np.where(live, np.maximum(hh - oe_ins, 0), 0)
+        fl = np.zeros((32, cpl), dtype=np.int64); run = np.zeros(32, dtype=np.int64)
+        for k in range(cpl):
+            fl[:, k] = run
+            run = np.maximum(run - e_ins, g[:, k])
+        estep = cpl * e_ins
+        P = run + estep * L32
+        d = 1
+        while d < 32:
+            o = np.concatenate([np.zeros(d, dtype=np.int64), P[:-d]])
+            P = np.where(L32 >= d, np.maximum(P, o), P); d <<= 1
+        Pex = np.concatenate([[0], P[:-1]])
+        u = np.where(L32 > 0, np.maximum(Pex - estep * (L32 - 1), 0), 0)
+        f = np.maximum(fl, u[:, None] - K[None, :] * e_ins)
+        h = np.maximum(hh, f)
+        t = np.maximum(h - oe_del, 0)
+        enew = np.maximum(s16(e - e_del), t)                                  # 16-bit half of the packed add-max
+        key = int(np.where(live, h * 65536 + col, -1).max())
+        hleft = np.concatenate([[fc], h[:-1, cpl - 1]])
+        hprev = np.concatenate([hleft[:, None], h[:, :-1]], axis=1)
+        hprev = np.where(col == j0, fc, hprev)
+        for l in range(32):
+            for k in range(cpl):
+                c = int(col[l, k])
+                if c <= lim: eh[c & rm] = pack(int(hprev[l, k]), int(enew[l, k]) if c < lim else 0)
+        mj = key & 0xffff
+        hlast = int(h[(lim - 1 - j0) // cpl, (lim - 1 - j0) % cpl])
+        z = live & (h == 0)
+        za = z & (col <= mj - 1); ze = z & (col >= mj + 1)
+        return key, hlast, (int(col[za].max()) if za.any() else -1), (int(col[ze].min()) if ze.any() else 0x7fffffff)
+
     for i in range(tlen):
         tb = int(target[i])
         j0 = max(beg, i - w); lim = min(end, i + w + 1, qlen)
@@ -154,6 +198,23 @@ def k2_model(p, query, target, h0, w, variant):
         if lim <= j0:
             if j0 == qlen and not gscore > fc: max_ie, gscore = i, fc
             break
+        if narrow and variant == 1 and lim - j0 < 64:
+            kmax, h1, cb, ce = narrow_row(1 if lim - j0 < 32 else 2, j0, lim, fc, tb)
+            m, mj = kmax >> 16, kmax & 0xffff
+            cells += lim - j0
+            if lim == qlen and not gscore > h1: max_ie, gscore = i, h1
+            if m == 0: break
+            if m > mx:
+                mx, max_i, max_j = m, i, mj
+                max_off = max(max_off, abs(mj - i))
+            elif zdrop > 0:
+                di, dj = i - max_i, mj - max_j
+                if di > dj:
+                    if mx - m - (di - dj) * e_del > zdrop: break
+                elif mx - m - (dj - di) * e_ins > zdrop: break
+            beg = cb + 2 if cb >= 0 else (j0 + 1 if fc == 0 else j0)
+            end = ce + 1 if ce != 0x7fffffff else lim + 1
+            continue
         span = lim - (j0 & ~7)
         wide12 = variant == 1 and 256 <= span < 384
         single = variant == 1 and (span < 256 or wide12)
@@ -222,9 +283,10 @@ def check(O, tasks, variant, **pk):
     for i in range(len(tasks["h0"])):
         qs = tasks["qbuf"][tasks["qoff"][i]:tasks["qoff"][i + 1]]; ts = tasks["tbuf"][tasks["toff"][i]:tasks["toff"][i + 1]]
         w = int(O.lib().bswref_clamp_w(C.byref(p), len(qs), int(tasks["w"][i]), p.end_bonus))
-        got = k2_model(p, qs, ts, int(tasks["h0"][i]), w, variant)
         want = tuple(int(ro[k][i]) for k in ("score", "qle", "tle", "gtle", "gscore", "max_off")) + (int(co[i]),)
-        assert got == want, (i, variant, pk, len(qs), len(ts), int(tasks["h0"][i]), w, got, want)
+        for narrow in ((False, True) if variant == 1 else (False,)):          # option k2_narrow = 0 / 1 (the default)
+            got = k2_model(p, qs, ts, int(tasks["h0"][i]), w, variant, narrow=narrow)
+            assert got == want, (i, variant, narrow, pk, len(qs), len(ts), int(tasks["h0"][i]), w, got, want)
 
 
 def near_matches(rng, n, qlo, qhi, h0, w, sub=0.02, tail=40):
